@@ -1,0 +1,172 @@
+// common.cuh — shared device/host helpers for libbodo_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "../../include/bodo_b200.h"
+
+namespace b200 {
+
+// Bodo_CTypes / bodo_array_type codes (reference: bodo/libs/_bodo_common.h:331-359, :515-532)
+enum CType : int { CT_INT8 = 0, CT_UINT8 = 1, CT_INT32 = 2, CT_UINT32 = 3, CT_INT64 = 4, CT_FLOAT32 = 5, CT_FLOAT64 = 6,
+                   CT_UINT64 = 7, CT_INT16 = 8, CT_UINT16 = 9, CT_BOOL = 11, CT_DATE = 13, CT_DATETIME = 15,
+                   CT_TIMEDELTA = 16 };
+enum ArrType : int { ARR_NUMPY = 0, ARR_NULLABLE = 2 };
+// Bodo_FTypes (reference: bodo/libs/groupby/_groupby_ftypes.h:17-110)
+enum FType : int { FT_SIZE = 4, FT_SUM = 6, FT_COUNT = 7, FT_MEAN = 14, FT_MIN = 15, FT_MAX = 16 };
+
+// hash seeds (reference: bodo/libs/_array_hash.h:8-14)
+constexpr uint32_t SEED_HASH_PARTITION = 0xb0d01289u;
+constexpr uint32_t SEED_HASH_JOIN = 0xb0d01286u;
+
+void set_last_error(const std::string& msg);
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define B200_CUDA(call)                                                                                       \
+    do {                                                                                                      \
+        cudaError_t _e = (call);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            throw b200::Error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " in " #call " at " +   \
+                              __FILE__ + ":" + std::to_string(__LINE__));                                     \
+    } while (0)
+
+#define B200_REQUIRE(cond, msg)                      \
+    do {                                             \
+        if (!(cond)) throw b200::Error(std::string(msg)); \
+    } while (0)
+
+inline int ctype_size(int ct) {
+    switch (ct) {
+        case CT_INT8: case CT_UINT8: case CT_BOOL: return 1;
+        case CT_INT16: case CT_UINT16: return 2;
+        case CT_INT32: case CT_UINT32: case CT_FLOAT32: case CT_DATE: return 4;
+        case CT_INT64: case CT_UINT64: case CT_FLOAT64: case CT_DATETIME: case CT_TIMEDELTA: return 8;
+        default: return 0;
+    }
+}
+inline bool ctype_is_float(int ct) { return ct == CT_FLOAT32 || ct == CT_FLOAT64; }
+inline bool ctype_is_signed_int(int ct) {
+    return ct == CT_INT8 || ct == CT_INT16 || ct == CT_INT32 || ct == CT_INT64 || ct == CT_DATE || ct == CT_DATETIME ||
+           ct == CT_TIMEDELTA;
+}
+
+// ---- device helpers -------------------------------------------------------------------------
+
+__device__ __forceinline__ bool bit_valid(const uint8_t* __restrict__ bm, int64_t i) {
+    return bm == nullptr || ((bm[i >> 3] >> (i & 7)) & 1);
+}
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+// XXH3_64bits_withSeed for 4- and 8-byte inputs (XXH3_len_4to8_64b + XXH3_rrmxmx), the function behind the
+// reference's hash_inner_32 (bodo/libs/vendored/_murmurhash3.h:59-68, vendored/xxhash.h:4034-4041,4102-4119).
+// Restated from the published xxHash algorithm; pinned against the reference's vendored header in
+// tests/test_oracle.py (through the oracle) and tests/test_gpu_shuffle.py (this device function).
+__host__ __device__ __forceinline__ uint64_t xxh3_64_short(uint64_t raw, int len, uint32_t seed32) {
+    uint64_t seed = seed32;
+    uint32_t s = (uint32_t)seed;
+    uint32_t sw = ((s & 0xffu) << 24) | ((s & 0xff00u) << 8) | ((s >> 8) & 0xff00u) | (s >> 24);
+    seed ^= (uint64_t)sw << 32;
+    uint32_t in1 = (uint32_t)raw;
+    uint32_t in2 = len == 8 ? (uint32_t)(raw >> 32) : (uint32_t)raw;
+    const uint64_t bitflip = (0x1cad21f72c81017cULL ^ 0xdb979083e96dd4deULL) - seed;
+    uint64_t h = ((uint64_t)in2 + ((uint64_t)in1 << 32)) ^ bitflip;
+    h ^= ((h << 49) | (h >> 15)) ^ ((h << 24) | (h >> 40));
+    h *= 0x9FB21C651E98DF25ULL;
+    h ^= (h >> 35) + (uint64_t)len;
+    h *= 0x9FB21C651E98DF25ULL;
+    return h ^ (h >> 28);
+}
+
+// hash_to_rank (reference: bodo/libs/_shuffle.h:5-7): (uint32) hash % n_pes.
+__host__ __device__ __forceinline__ int hash_to_rank_u32(uint32_t h, int n_pes) { return (int)(h % (uint32_t)n_pes); }
+
+// Table-slot hash: the same xxh3 value (one hash per row); ranks use the low 32 bits, slots the high 32
+// bits, so the two are independent (a rank's keys all share low32 % P).
+__device__ __forceinline__ uint64_t key_hash(int64_t key) { return xxh3_64_short((uint64_t)key, 8, SEED_HASH_PARTITION); }
+
+__device__ __forceinline__ int64_t load_int_as_i64(const void* __restrict__ p, int ct, int64_t i) {
+    switch (ct) {
+        case CT_INT64: case CT_DATETIME: case CT_TIMEDELTA: case CT_UINT64: return ((const int64_t*)p)[i];
+        case CT_INT32: case CT_DATE: return ((const int32_t*)p)[i];
+        case CT_UINT32: return ((const uint32_t*)p)[i];
+        case CT_INT16: return ((const int16_t*)p)[i];
+        case CT_UINT16: return ((const uint16_t*)p)[i];
+        case CT_INT8: return ((const int8_t*)p)[i];
+        case CT_UINT8: case CT_BOOL: return ((const uint8_t*)p)[i];
+        default: return 0;
+    }
+}
+__device__ __forceinline__ double load_as_f64(const void* __restrict__ p, int ct, int64_t i) {
+    switch (ct) {
+        case CT_FLOAT64: return ((const double*)p)[i];
+        case CT_FLOAT32: return (double)((const float*)p)[i];
+        default: return (double)load_int_as_i64(p, ct, i);
+    }
+}
+
+// order-preserving double <-> uint64 encoding (so float min/max are native 64-bit integer atomics)
+__host__ __device__ __forceinline__ uint64_t f64_to_ordered(double d) {
+#ifdef __CUDA_ARCH__
+    uint64_t b = (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t b; memcpy(&b, &d, 8);
+#endif
+    return b ^ ((b >> 63) ? 0xFFFFFFFFFFFFFFFFULL : 0x8000000000000000ULL);
+}
+__host__ __device__ __forceinline__ double ordered_to_f64(uint64_t e) {
+    uint64_t b = e ^ ((e >> 63) ? 0x8000000000000000ULL : 0xFFFFFFFFFFFFFFFFULL);
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double d; memcpy(&d, &b, 8); return d;
+#endif
+}
+
+// counter-based generator of the synthetic workload; mirrored in oracle/bodo_oracle.c
+// (oracle_synth_fill) and bodo_b200/synth.py.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x += 0x9e3779b97f4a7c15ULL;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+    return x ^ (x >> 31);
+}
+
+inline int num_sms(int device) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    return n > 0 ? n : 148;
+}
+
+// RAII device buffer on a fixed device (plain cudaMalloc: allocations happen at state set-up / growth
+// time, never per batch on the steady-state path).
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void alloc(size_t n) {
+        release();
+        if (n == 0) n = 8;
+        B200_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    void ensure(size_t n) { if (n > bytes) alloc(n); }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+}  // namespace b200

@@ -1,0 +1,1009 @@
+// groupby.cu — streaming hash groupby/aggregate on one B200 (sm_100a).
+//
+// Replaces GroupbyState + groupby_agg_build_consume_batch + FinalizeBuild of the reference
+// (bodo/libs/streaming/_groupby.cpp:2554-3031, 4325-4457, 4062-4256) and the aggregate kernels of
+// bodo/libs/groupby/_groupby_agg_funcs.h.  Design:
+//   * one persistent open-addressing table per state (linear probing, load <= 0.5, int64 keys,
+//     SoA accumulator columns), instead of the reference's per-batch update table + combine;
+//   * the consume kernel fuses hash + find-or-insert + every aggregate update of a row;
+//   * rows whose insert would overfill the table are appended to a fail list; the host grows/rehashes
+//     the table and replays only those rows (the reference's transactional retry,
+//     _groupby.cpp:3309-3341, without the partition split);
+//   * finalize compacts occupied slots and evaluates the output columns (mean_eval etc.).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr long long EMPTY_KEY = (long long)0x8000000000000000ULL;  // INT64_MIN marks a free slot
+constexpr int MAX_OPS = 12;
+constexpr int64_t CHUNK_ROWS = 1ll << 27;  // rows per kernel launch (bounds the fail list at 512 MiB)
+
+enum OpKind : int { K_SUM_I64 = 0, K_SUM_F64, K_COUNT, K_SIZE, K_MEAN, K_MIN_I64, K_MAX_I64, K_MIN_F64, K_MAX_F64 };
+
+struct OpDesc {
+    int kind;
+    int in_ctype;
+    const void* in_data;
+    const uint8_t* in_valid;
+    void* a0;  // main accumulator column (8 B / slot)
+    void* a1;  // second accumulator (mean count, min/max seen-count) or nullptr
+};
+
+struct ConsumeArgs {
+    const void* key_data;
+    const uint8_t* key_valid;
+    int key_ctype;
+    int dropna;
+    int64_t n_rows;
+    const uint32_t* index_list;  // nullptr: rows [0, n_rows); else replay of the listed rows
+    long long* tkeys;
+    uint64_t cap;  // power of two; slot cap = NA key, slot cap + 1 = the key equal to EMPTY_KEY
+    long long* counters;  // [0] groups in table, [1] failed rows, [2] cursor, [3] NA present, [4] EMPTY_KEY present
+    long long group_limit;
+    uint32_t* fail_list;
+    int n_ops;
+    OpDesc ops[MAX_OPS];
+};
+
+// find-or-insert; returns slot or UINT64_MAX when the table is at its group limit
+__device__ __forceinline__ uint64_t find_or_insert(long long* __restrict__ tkeys, uint64_t cap, long long key,
+                                                   long long* counters, long long group_limit) {
+    uint64_t mask = cap - 1;
+    uint64_t s = (key_hash(key) >> 32) & mask;
+    for (uint64_t probes = 0; probes <= mask; probes++) {
+        long long k = __ldcg(tkeys + s);
+        if (k == key) return s;
+        if (k == EMPTY_KEY) {
+            // take a ticket first so the table can never exceed group_limit (probing always terminates)
+            long long t = atomicAdd((unsigned long long*)&counters[0], 1ull);
+            if (t >= group_limit) {
+                atomicAdd((unsigned long long*)&counters[0], (unsigned long long)-1ll);
+                return ~0ull;
+            }
+            long long prev = atomicCAS((unsigned long long*)(tkeys + s), (unsigned long long)EMPTY_KEY,
+                                       (unsigned long long)key);
+            if (prev == EMPTY_KEY) return s;
+            atomicAdd((unsigned long long*)&counters[0], (unsigned long long)-1ll);  // lost the race: hand the ticket back
+            if (prev == key) return s;
+        }
+        s = (s + 1) & mask;
+    }
+    return ~0ull;
+}
+
+__device__ __forceinline__ void apply_ops(const ConsumeArgs& a, uint64_t slot, int64_t row) {
+#pragma unroll 1
+    for (int j = 0; j < a.n_ops; j++) {
+        const OpDesc& op = a.ops[j];
+        if (op.kind == K_SIZE) {  // size_agg (_groupby_agg_funcs.h:661-669): counts every row
+            atomicAdd((unsigned long long*)op.a0 + slot, 1ull);
+            continue;
+        }
+        if (!bit_valid(op.in_valid, row)) continue;  // nullable input: skip NA (do_apply_to_column.cpp:1796-1823)
+        switch (op.kind) {
+            case K_SUM_I64:  // casted_aggfunc sum: int64 accumulate, wraparound (_groupby_agg_funcs.h:176-190)
+                atomicAdd((unsigned long long*)op.a0 + slot, (unsigned long long)load_int_as_i64(op.in_data, op.in_ctype, row));
+                break;
+            case K_COUNT: {  // count_agg (:644-657): non-NA values (NaN is NA for floats)
+                bool ok = true;
+                if (op.in_ctype == CT_FLOAT64 || op.in_ctype == CT_FLOAT32) ok = !isnan(load_as_f64(op.in_data, op.in_ctype, row));
+                if (ok) atomicAdd((unsigned long long*)op.a0 + slot, 1ull);
+                break;
+            }
+            case K_SUM_F64: {
+                double v = load_as_f64(op.in_data, op.in_ctype, row);
+                if (!isnan(v)) atomicAdd((double*)op.a0 + slot, v);
+                break;
+            }
+            case K_MEAN: {  // mean_agg (:673-689): double sum + uint64 count
+                double v = load_as_f64(op.in_data, op.in_ctype, row);
+                if (!isnan(v)) {
+                    atomicAdd((double*)op.a0 + slot, v);
+                    atomicAdd((unsigned long long*)op.a1 + slot, 1ull);
+                }
+                break;
+            }
+            case K_MIN_I64:
+                atomicMin((long long*)op.a0 + slot, (long long)load_int_as_i64(op.in_data, op.in_ctype, row));
+                if (op.a1) atomicAdd((unsigned long long*)op.a1 + slot, 1ull);
+                break;
+            case K_MAX_I64:
+                atomicMax((long long*)op.a0 + slot, (long long)load_int_as_i64(op.in_data, op.in_ctype, row));
+                if (op.a1) atomicAdd((unsigned long long*)op.a1 + slot, 1ull);
+                break;
+            case K_MIN_F64: {
+                double v = load_as_f64(op.in_data, op.in_ctype, row);
+                if (!isnan(v)) {
+                    atomicMin((unsigned long long*)op.a0 + slot, f64_to_ordered(v));
+                    if (op.a1) atomicAdd((unsigned long long*)op.a1 + slot, 1ull);
+                }
+                break;
+            }
+            case K_MAX_F64: {
+                double v = load_as_f64(op.in_data, op.in_ctype, row);
+                if (!isnan(v)) {
+                    atomicMax((unsigned long long*)op.a0 + slot, f64_to_ordered(v));
+                    if (op.a1) atomicAdd((unsigned long long*)op.a1 + slot, 1ull);
+                }
+                break;
+            }
+        }
+    }
+}
+
+// Generic fused consume kernel: any key/value types, any mix of aggregates, nullable columns.
+__global__ void __launch_bounds__(256) groupby_consume_kernel(const __grid_constant__ ConsumeArgs a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_rows; i += stride) {
+        int64_t row = a.index_list ? (int64_t)a.index_list[i] : i;
+        bool kvalid = bit_valid(a.key_valid, row);
+        uint64_t slot;
+        if (!kvalid) {
+            if (a.dropna) continue;  // filter_na_keys (_groupby.cpp:4278-4309)
+            slot = a.cap;
+            a.counters[3] = 1;
+        } else {
+            long long key = load_int_as_i64(a.key_data, a.key_ctype, row);
+            if (key == EMPTY_KEY) {
+                slot = a.cap + 1;
+                a.counters[4] = 1;
+            } else {
+                slot = find_or_insert(a.tkeys, a.cap, key, a.counters, a.group_limit);
+                if (slot == ~0ull) {
+                    unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
+                    a.fail_list[f] = (uint32_t)row;
+                    continue;
+                }
+            }
+        }
+        apply_ops(a, slot, row);
+    }
+}
+
+// Specialised consume kernel for the headline shape: non-null int64 key, non-null int64 value,
+// aggregates drawn from {sum, count, size} of that one value column (BASELINE.json C1/C2).
+// Two rows per thread per iteration through 128-bit loads; the aggregate updates are `red` (no return).
+template <bool HAS_SUM, bool HAS_CNT>
+__global__ void __launch_bounds__(256) groupby_consume_i64_sumcount_kernel(
+    const long long* __restrict__ keys, const long long* __restrict__ vals, int64_t n_rows, long long* tkeys, uint64_t cap,
+    unsigned long long* acc_sum, unsigned long long* acc_cnt, long long* counters, long long group_limit,
+    uint32_t* fail_list) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+    int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 2;
+    for (; i < n_rows; i += stride) {
+        long long k[2], v[2];
+        int m = 2;
+        if (i + 1 < n_rows) {
+            longlong2 kk = __ldcs(reinterpret_cast<const longlong2*>(keys + i));
+            k[0] = kk.x; k[1] = kk.y;
+            if (HAS_SUM) { longlong2 vv = __ldcs(reinterpret_cast<const longlong2*>(vals + i)); v[0] = vv.x; v[1] = vv.y; }
+        } else {
+            k[0] = keys[i]; k[1] = 0; m = 1;
+            if (HAS_SUM) { v[0] = vals[i]; v[1] = 0; }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (r >= m) break;
+            uint64_t slot;
+            if (k[r] == EMPTY_KEY) {
+                slot = cap + 1;
+                counters[4] = 1;
+            } else {
+                slot = find_or_insert(tkeys, cap, k[r], counters, group_limit);
+                if (slot == ~0ull) {
+                    unsigned long long f = atomicAdd((unsigned long long*)&counters[1], 1ull);
+                    fail_list[f] = (uint32_t)(i + r);
+                    continue;
+                }
+            }
+            if (HAS_SUM) atomicAdd(acc_sum + slot, (unsigned long long)v[r]);
+            if (HAS_CNT) atomicAdd(acc_cnt + slot, 1ull);
+        }
+    }
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, uint64_t n, unsigned long long v) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+struct RehashArgs {
+    const long long* old_keys;
+    uint64_t old_cap;
+    long long* new_keys;
+    uint64_t new_cap;
+    int n_acc;
+    const unsigned long long* old_acc[2 * MAX_OPS];
+    unsigned long long* new_acc[2 * MAX_OPS];
+};
+// grow: re-insert every occupied slot (and the two special slots) into the new arrays
+__global__ void rehash_kernel(const __grid_constant__ RehashArgs a) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < a.old_cap + 2; s += stride) {
+        uint64_t ns;
+        if (s >= a.old_cap) {
+            ns = a.new_cap + (s - a.old_cap);
+        } else {
+            long long k = a.old_keys[s];
+            if (k == EMPTY_KEY) continue;
+            uint64_t mask = a.new_cap - 1;
+            ns = (key_hash(k) >> 32) & mask;
+            while (true) {
+                long long prev = atomicCAS((unsigned long long*)(a.new_keys + ns), (unsigned long long)EMPTY_KEY, (unsigned long long)k);
+                if (prev == EMPTY_KEY) break;
+                ns = (ns + 1) & mask;
+            }
+        }
+        for (int j = 0; j < a.n_acc; j++) a.new_acc[j][ns] = a.old_acc[j][s];
+    }
+}
+
+// ---- finalize: compact occupied slots, then evaluate output columns ----
+__global__ void compact_slots_kernel(const long long* __restrict__ tkeys, uint64_t cap, int na_present, int empty_present,
+                                     long long* cursor, uint64_t* slot_of_out) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s0 < ((cap + 2 + 31) & ~31ull); s0 += stride) {
+        bool occ = false;
+        if (s0 < cap) occ = tkeys[s0] != EMPTY_KEY;
+        else if (s0 == cap) occ = na_present;
+        else if (s0 == cap + 1) occ = empty_present;
+        unsigned m = __ballot_sync(0xffffffffu, occ);
+        int lane = threadIdx.x & 31;
+        long long base = 0;
+        if (lane == 0 && m) base = (long long)atomicAdd((unsigned long long*)cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (occ) slot_of_out[base + __popc(m & ((1u << lane) - 1))] = s0;
+    }
+}
+
+struct OutDesc {
+    int kind;       // OpKind
+    int out_ctype;  // CType of the output column
+    const void* a0;
+    const void* a1;
+    void* out_data;
+    uint32_t* out_valid;  // validity bitmap as 32-bit words, or nullptr when the column has no nulls
+};
+struct EvalArgs {
+    const long long* tkeys;
+    uint64_t cap;
+    const uint64_t* slot_of_out;
+    int64_t n_out;
+    int key_ctype;
+    void* out_keys;
+    uint32_t* out_key_valid;  // nullptr unless the NA-key group can exist
+    int n_ops;
+    OutDesc ops[MAX_OPS];
+};
+
+__device__ __forceinline__ void store_int_typed(void* p, int ct, int64_t i, long long v) {
+    switch (ct) {
+        case CT_INT64: case CT_UINT64: case CT_DATETIME: case CT_TIMEDELTA: ((long long*)p)[i] = v; break;
+        case CT_INT32: case CT_UINT32: case CT_DATE: ((int32_t*)p)[i] = (int32_t)v; break;
+        case CT_INT16: case CT_UINT16: ((int16_t*)p)[i] = (int16_t)v; break;
+        case CT_INT8: case CT_UINT8: case CT_BOOL: ((int8_t*)p)[i] = (int8_t)v; break;
+    }
+}
+__device__ __forceinline__ void store_f_typed(void* p, int ct, int64_t i, double v) {
+    if (ct == CT_FLOAT32) ((float*)p)[i] = (float)v; else ((double*)p)[i] = v;
+}
+
+// eval_groupby_funcs_helper (_groupby.cpp:396-457) + output null rules (aggfunc_output_initialize_kernel,
+// groupby/_groupby_common.cpp:50-74: sum/count/size valid, min/max/mean NULL when nothing was seen).
+__global__ void eval_output_kernel(const __grid_constant__ EvalArgs a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t n_round = (a.n_out + 31) & ~31ll;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_round; p += stride) {
+        bool in = p < a.n_out;
+        uint64_t s = in ? a.slot_of_out[p] : 0;
+        bool key_ok = true;
+        if (in) {
+            long long key = s < a.cap ? a.tkeys[s] : (s == a.cap ? 0 : EMPTY_KEY);
+            key_ok = s != a.cap;
+            store_int_typed(a.out_keys, a.key_ctype, p, key);
+        }
+        if (a.out_key_valid) {
+            unsigned m = __ballot_sync(0xffffffffu, in && key_ok);
+            if ((threadIdx.x & 31) == 0) a.out_key_valid[p >> 5] = m;
+        }
+#pragma unroll 1
+        for (int j = 0; j < a.n_ops; j++) {
+            const OutDesc& op = a.ops[j];
+            bool valid = in;
+            if (in) {
+                switch (op.kind) {
+                    case K_SUM_I64: case K_COUNT: case K_SIZE:
+                        store_int_typed(op.out_data, op.out_ctype, p, ((const long long*)op.a0)[s]);
+                        break;
+                    case K_SUM_F64:
+                        store_f_typed(op.out_data, op.out_ctype, p, ((const double*)op.a0)[s]);
+                        break;
+                    case K_MEAN: {  // mean_eval (do_apply_to_column.cpp:880-913)
+                        unsigned long long c = ((const unsigned long long*)op.a1)[s];
+                        valid = c > 0;
+                        store_f_typed(op.out_data, op.out_ctype, p, valid ? ((const double*)op.a0)[s] / (double)c : __longlong_as_double(0x7ff8000000000000ll));
+                        break;
+                    }
+                    case K_MIN_I64: case K_MAX_I64: {
+                        if (op.a1) valid = ((const unsigned long long*)op.a1)[s] > 0;
+                        store_int_typed(op.out_data, op.out_ctype, p, valid ? ((const long long*)op.a0)[s] : 0);
+                        break;
+                    }
+                    case K_MIN_F64: case K_MAX_F64: {
+                        unsigned long long e = ((const unsigned long long*)op.a0)[s];
+                        bool seen = op.kind == K_MIN_F64 ? (e != ~0ull) : (e != 0ull);
+                        if (op.a1) valid = seen;
+                        store_f_typed(op.out_data, op.out_ctype, p, seen ? ordered_to_f64(e) : __longlong_as_double(0x7ff8000000000000ll));
+                        break;
+                    }
+                }
+            }
+            if (op.out_valid) {
+                unsigned m = __ballot_sync(0xffffffffu, valid);
+                if ((threadIdx.x & 31) == 0) op.out_valid[p >> 5] = m;
+            }
+        }
+    }
+}
+
+// ---- multi-rank exchange: pack partial aggregates per destination rank -------------------------
+// Wire format of one partial row (all fields 8 bytes): [key][flags: bit0 = key valid][a0, a1 of op 0]...
+// Only accumulators that exist are sent (row width = 16 + 8 * n_acc).
+struct PackArgs {
+    const long long* tkeys;
+    uint64_t cap;
+    const uint64_t* slot_of_out;
+    int64_t n_out;
+    int n_pes;
+    int n_acc;
+    const unsigned long long* acc[2 * MAX_OPS];
+    long long* dest_count;   // n_pes (histogram pass) / running cursors (scatter pass)
+    unsigned long long* out; // packed rows
+    int row_words;
+    int pass;                // 0 = histogram, 1 = scatter
+};
+__global__ void pack_partials_kernel(const __grid_constant__ PackArgs a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t na_hash = (uint32_t)xxh3_64_short(1ull, 8, SEED_HASH_PARTITION);  // hash_na_val (_array_hash.cpp:22-29)
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < a.n_out; p += stride) {
+        uint64_t s = a.slot_of_out[p];
+        long long key = s < a.cap ? a.tkeys[s] : (s == a.cap ? 0 : EMPTY_KEY);
+        bool kvalid = s != a.cap;
+        uint32_t h = kvalid ? (uint32_t)key_hash(key) : na_hash;
+        int d = hash_to_rank_u32(h, a.n_pes);
+        if (a.pass == 0) {
+            atomicAdd((unsigned long long*)&a.dest_count[d], 1ull);
+        } else {
+            long long pos = (long long)atomicAdd((unsigned long long*)&a.dest_count[d], 1ull);
+            unsigned long long* o = a.out + pos * a.row_words;
+            o[0] = (unsigned long long)key;
+            o[1] = kvalid ? 1ull : 0ull;
+            for (int j = 0; j < a.n_acc; j++) o[2 + j] = a.acc[j][s];
+        }
+    }
+}
+
+struct CombineArgs {
+    const unsigned long long* in;
+    int64_t n_rows;
+    int row_words;
+    long long* tkeys;
+    uint64_t cap;
+    long long* counters;
+    long long group_limit;
+    uint32_t* fail_list;
+    const uint32_t* index_list;
+    int n_ops;
+    int kinds[MAX_OPS];
+    void* a0[MAX_OPS];
+    void* a1[MAX_OPS];
+};
+// combine step (get_combine_func, groupby/_groupby_update.cpp:41-57): count/size/mean -> sum, min -> min, max -> max
+__global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_rows; i += stride) {
+        int64_t row = a.index_list ? (int64_t)a.index_list[i] : i;
+        const unsigned long long* r = a.in + row * a.row_words;
+        long long key = (long long)r[0];
+        bool kvalid = r[1] & 1;
+        uint64_t slot;
+        if (!kvalid) { slot = a.cap; a.counters[3] = 1; }
+        else if (key == EMPTY_KEY) { slot = a.cap + 1; a.counters[4] = 1; }
+        else {
+            slot = find_or_insert(a.tkeys, a.cap, key, a.counters, a.group_limit);
+            if (slot == ~0ull) {
+                unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
+                a.fail_list[f] = (uint32_t)row;
+                continue;
+            }
+        }
+        int w = 2;
+        for (int j = 0; j < a.n_ops; j++) {
+            unsigned long long v0 = r[w++];
+            unsigned long long v1 = a.a1[j] ? r[w++] : 0;
+            switch (a.kinds[j]) {
+                case K_SUM_I64: case K_COUNT: case K_SIZE: atomicAdd((unsigned long long*)a.a0[j] + slot, v0); break;
+                case K_SUM_F64: atomicAdd((double*)a.a0[j] + slot, __longlong_as_double((long long)v0)); break;
+                case K_MEAN:
+                    atomicAdd((double*)a.a0[j] + slot, __longlong_as_double((long long)v0));
+                    atomicAdd((unsigned long long*)a.a1[j] + slot, v1);
+                    break;
+                case K_MIN_I64: atomicMin((long long*)a.a0[j] + slot, (long long)v0); break;
+                case K_MAX_I64: atomicMax((long long*)a.a0[j] + slot, (long long)v0); break;
+                case K_MIN_F64: atomicMin((unsigned long long*)a.a0[j] + slot, v0); break;
+                case K_MAX_F64: atomicMax((unsigned long long*)a.a0[j] + slot, v0); break;
+            }
+            if (a.a1[j] && a.kinds[j] != K_MEAN) atomicAdd((unsigned long long*)a.a1[j] + slot, v1);
+        }
+    }
+}
+
+// ================================================================================================
+// Host side
+// ================================================================================================
+
+struct FuncSpec {
+    int ftype;
+    int in_col;  // physical input column or -1 (size)
+    int in_ctype;
+    int in_arrtype;
+    int kind;
+    int out_ctype;
+    int out_arrtype;
+    bool has_a1;
+    unsigned long long init0;
+};
+
+class GroupbyState {
+   public:
+    int device;
+    cudaStream_t stream;
+    cudaStream_t copy_stream = nullptr;
+    int n_cols;
+    std::vector<int8_t> c_types, arr_types;
+    int n_funcs;
+    std::vector<FuncSpec> funcs;
+    bool dropna, parallel;
+    int n_pes, rank;
+    int64_t output_batch_size;
+    int sms;
+
+    uint64_t cap = 0;
+    DevBuf d_keys;
+    std::vector<DevBuf> d_a0, d_a1;
+    DevBuf d_counters;
+    long long* h_counters = nullptr;  // pinned
+    DevBuf d_fail;
+    int64_t n_groups = 0;
+
+    // host-input staging (double buffered, per used column)
+    std::vector<DevBuf> stage[2];
+    cudaEvent_t stage_free[2] = {nullptr, nullptr}, stage_ready[2] = {nullptr, nullptr};
+
+    // finalize / output
+    bool finalized = false;
+    int64_t n_out = 0, out_cursor = 0;
+    DevBuf d_slot_of_out, d_out_keys, d_out_key_valid;
+    std::vector<DevBuf> d_out_data, d_out_valid;
+    // exchange
+    DevBuf d_dest_count;
+    std::vector<long long> h_dest_count;
+    int64_t packed_rows = 0;
+
+    // metrics
+    int64_t rows_consumed = 0, rebuilds = 0, launches = 0, fail_rows = 0;
+    bool build_done = false;
+
+    GroupbyState(const int8_t* ct, const int8_t* at, int n_arrs, const int32_t* ftypes, const int32_t* f_in_offsets,
+                 const int32_t* f_in_cols, int n_funcs_, uint64_t n_keys, int64_t out_bs, bool parallel_, bool dropna_,
+                 int device_, int n_pes_, int rank_, int64_t expected_groups, cudaStream_t stream_)
+        : device(device_), stream(stream_), n_cols(n_arrs), n_funcs(n_funcs_), dropna(dropna_), parallel(parallel_),
+          n_pes(n_pes_), rank(rank_), output_batch_size(out_bs) {
+        B200_REQUIRE(n_keys == 1, "b200 groupby: exactly one key column is supported (multi-key is a 'next' row, SURVEY.md §8f)");
+        B200_REQUIRE(n_arrs >= 1, "b200 groupby: empty build schema");
+        B200_REQUIRE(n_funcs_ <= MAX_OPS, "b200 groupby: too many aggregate functions");
+        c_types.assign(ct, ct + n_arrs);
+        arr_types.assign(at, at + n_arrs);
+        int kct = c_types[0];
+        B200_REQUIRE(ctype_size(kct) > 0 && !ctype_is_float(kct), "b200 groupby: key column must be an integer/date type");
+        B200_REQUIRE(arr_types[0] == ARR_NUMPY || arr_types[0] == ARR_NULLABLE, "b200 groupby: unsupported key array type");
+        if (!parallel) { n_pes = 1; rank = 0; }
+        B200_CUDA(cudaSetDevice(device));
+        sms = num_sms(device);
+        for (int j = 0; j < n_funcs; j++) {
+            FuncSpec f{};
+            f.ftype = ftypes[j];
+            int n_in = f_in_offsets[j + 1] - f_in_offsets[j];
+            B200_REQUIRE(n_in <= 1, "b200 groupby: functions with more than one input column are not supported");
+            f.in_col = n_in == 1 ? f_in_cols[f_in_offsets[j]] : -1;
+            if (f.ftype != FT_SIZE) B200_REQUIRE(f.in_col >= 1 && f.in_col < n_arrs, "b200 groupby: bad f_in_cols entry");
+            f.in_ctype = f.in_col >= 0 ? c_types[f.in_col] : CT_INT64;
+            f.in_arrtype = f.in_col >= 0 ? arr_types[f.in_col] : ARR_NUMPY;
+            B200_REQUIRE(f.in_arrtype == ARR_NUMPY || f.in_arrtype == ARR_NULLABLE, "b200 groupby: unsupported value array type");
+            B200_REQUIRE(ctype_size(f.in_ctype) > 0, "b200 groupby: unsupported value dtype");
+            bool isf = ctype_is_float(f.in_ctype);
+            f.has_a1 = false;
+            f.init0 = 0;
+            // output typing: get_groupby_output_dtype (groupby/_groupby_common.cpp:561-668)
+            switch (f.ftype) {
+                case FT_SIZE: f.kind = K_SIZE; f.out_ctype = CT_INT64; f.out_arrtype = ARR_NUMPY; break;
+                case FT_COUNT: f.kind = K_COUNT; f.out_ctype = CT_INT64; f.out_arrtype = ARR_NUMPY; break;
+                case FT_SUM:
+                    f.kind = isf ? K_SUM_F64 : K_SUM_I64;
+                    f.out_ctype = isf ? f.in_ctype : (ctype_is_signed_int(f.in_ctype) || f.in_ctype == CT_BOOL ? CT_INT64 : CT_UINT64);
+                    f.out_arrtype = f.in_ctype == CT_BOOL ? ARR_NULLABLE : f.in_arrtype;
+                    break;
+                case FT_MEAN: f.kind = K_MEAN; f.out_ctype = CT_FLOAT64; f.out_arrtype = ARR_NULLABLE; f.has_a1 = true; break;
+                case FT_MIN: case FT_MAX: {
+                    B200_REQUIRE(f.in_ctype != CT_UINT64, "b200 groupby: min/max of uint64 is not supported");
+                    bool mn = f.ftype == FT_MIN;
+                    f.kind = isf ? (mn ? K_MIN_F64 : K_MAX_F64) : (mn ? K_MIN_I64 : K_MAX_I64);
+                    f.out_ctype = f.in_ctype; f.out_arrtype = f.in_arrtype;
+                    f.has_a1 = f.in_arrtype == ARR_NULLABLE;
+                    if (isf) f.init0 = mn ? ~0ull : 0ull;
+                    else f.init0 = mn ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
+                    break;
+                }
+                default:
+                    throw Error("b200 groupby: unsupported aggregate function ftype=" + std::to_string(f.ftype) +
+                                " (supported: size, sum, count, mean, min, max)");
+            }
+            funcs.push_back(f);
+        }
+        d_a0.resize(n_funcs); d_a1.resize(n_funcs);
+        d_out_data.resize(n_funcs); d_out_valid.resize(n_funcs);
+        d_counters.alloc(8 * sizeof(long long));
+        B200_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(long long), stream));
+        B200_CUDA(cudaMallocHost((void**)&h_counters, 8 * sizeof(long long)));
+        uint64_t want = 1ull << 16;
+        if (expected_groups > 0) { while (want < (uint64_t)expected_groups * 2) want <<= 1; }
+        else want = 1ull << 21;
+        alloc_table(want, d_keys, d_a0, d_a1);
+        cap = want;
+    }
+
+    ~GroupbyState() {
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        for (int b = 0; b < 2; b++) { if (stage_free[b]) cudaEventDestroy(stage_free[b]); if (stage_ready[b]) cudaEventDestroy(stage_ready[b]); }
+        if (h_counters) cudaFreeHost(h_counters);
+    }
+
+    int grid_for(int64_t n, int per_thread = 1, int block = 256) const {
+        int64_t want = (n + (int64_t)block * per_thread - 1) / ((int64_t)block * per_thread);
+        int64_t maxg = (int64_t)sms * 8;  // 8 resident CTAs of 256 threads per SM
+        return (int)std::max<int64_t>(1, std::min(want, maxg));
+    }
+
+    void fill(void* p, uint64_t n, unsigned long long v) {
+        if (v == 0) { B200_CUDA(cudaMemsetAsync(p, 0, n * 8, stream)); return; }
+        fill_u64_kernel<<<grid_for((int64_t)n), 256, 0, stream>>>((unsigned long long*)p, n, v);
+        launches++;
+    }
+
+    void alloc_table(uint64_t c, DevBuf& keys, std::vector<DevBuf>& a0, std::vector<DevBuf>& a1) {
+        B200_REQUIRE(c <= (1ull << 32), "b200 groupby: hash table would exceed 2^32 slots");
+        keys.alloc((c + 2) * 8);
+        fill(keys.p, c + 2, (unsigned long long)EMPTY_KEY);
+        for (int j = 0; j < n_funcs; j++) {
+            a0[j].alloc((c + 2) * 8);
+            fill(a0[j].p, c + 2, funcs[j].init0);
+            if (funcs[j].has_a1) { a1[j].alloc((c + 2) * 8); fill(a1[j].p, c + 2, 0); }
+        }
+    }
+
+    void read_counters() {
+        B200_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        B200_CUDA(cudaStreamSynchronize(stream));
+        n_groups = h_counters[0];
+    }
+
+    void grow(uint64_t new_cap) {
+        DevBuf nk; std::vector<DevBuf> na0(n_funcs), na1(n_funcs);
+        alloc_table(new_cap, nk, na0, na1);
+        RehashArgs ra{};
+        ra.old_keys = d_keys.as<long long>(); ra.old_cap = cap; ra.new_keys = nk.as<long long>(); ra.new_cap = new_cap;
+        int n = 0;
+        for (int j = 0; j < n_funcs; j++) {
+            ra.old_acc[n] = d_a0[j].as<unsigned long long>(); ra.new_acc[n++] = na0[j].as<unsigned long long>();
+            if (funcs[j].has_a1) { ra.old_acc[n] = d_a1[j].as<unsigned long long>(); ra.new_acc[n++] = na1[j].as<unsigned long long>(); }
+        }
+        ra.n_acc = n;
+        rehash_kernel<<<grid_for((int64_t)cap + 2), 256, 0, stream>>>(ra);
+        launches++;
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaStreamSynchronize(stream));  // old arrays are freed below
+        d_keys = std::move(nk);
+        for (int j = 0; j < n_funcs; j++) { d_a0[j] = std::move(na0[j]); d_a1[j] = std::move(na1[j]); }
+        cap = new_cap;
+        rebuilds++;
+    }
+
+    // After a launch that may have failed rows: grow + replay until every row is in.
+    template <typename Replay>
+    void settle(int64_t chunk_rows, bool could_fail, Replay replay) {
+        if (!could_fail) return;
+        read_counters();
+        while (h_counters[1] > 0) {
+            int64_t nf = h_counters[1];
+            fail_rows += nf;
+            uint64_t nc = cap;
+            while (nc < 2ull * (uint64_t)(n_groups + nf)) nc <<= 1;
+            if (nc == cap) nc <<= 1;
+            grow(nc);
+            // the fail list becomes the index list of the replay; it cannot fail again (room for nf new groups)
+            DevBuf replay_list;
+            replay_list.alloc((size_t)nf * 4);
+            B200_CUDA(cudaMemcpyAsync(replay_list.p, d_fail.p, (size_t)nf * 4, cudaMemcpyDeviceToDevice, stream));
+            B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8, 0, 8, stream));
+            replay(replay_list.as<uint32_t>(), nf);
+            read_counters();
+        }
+        (void)chunk_rows;
+    }
+
+    // Consume rows [0, n) of device-resident columns.
+    void consume_device_chunk(const std::vector<const void*>& data, const std::vector<const uint8_t*>& valid, int64_t n) {
+        if (n == 0) return;
+        bool could_fail = (int64_t)(cap / 2) - n_groups_bound < n;
+        if (could_fail) d_fail.ensure((size_t)n * 4);
+        // fast path: non-null int64 key + {sum, count/size} over one non-null int64 value column
+        bool fast = c_types[0] == CT_INT64 && valid[0] == nullptr && n_funcs >= 1;
+        int sum_j = -1, cnt_j = -1, vcol = -1;
+        for (int j = 0; j < n_funcs && fast; j++) {
+            const FuncSpec& f = funcs[j];
+            if (f.kind == K_SUM_I64 && f.in_ctype == CT_INT64 && valid[f.in_col] == nullptr && sum_j < 0) {
+                sum_j = j; vcol = f.in_col;
+            } else if ((f.kind == K_SIZE || (f.kind == K_COUNT && !ctype_is_float(f.in_ctype) && valid[f.in_col] == nullptr)) && cnt_j < 0) {
+                cnt_j = j;
+            } else {
+                fast = false;
+            }
+        }
+        if (fast && (((uintptr_t)data[0] & 15) || (vcol >= 0 && ((uintptr_t)data[vcol] & 15)))) fast = false;
+        // table pointers are looked up at launch time: grow() replaces them between a launch and its replay
+        auto launch = [&](const uint32_t* index_list, int64_t rows) {
+            long long* ctr = d_counters.as<long long>();
+            long long limit = (long long)(cap / 2);
+            if (fast && index_list == nullptr) {
+                int g = grid_for(rows, 2);
+                const long long* k = (const long long*)data[0];
+                const long long* v = vcol >= 0 ? (const long long*)data[vcol] : nullptr;
+                unsigned long long* as = sum_j >= 0 ? d_a0[sum_j].as<unsigned long long>() : nullptr;
+                unsigned long long* ac = cnt_j >= 0 ? d_a0[cnt_j].as<unsigned long long>() : nullptr;
+                if (sum_j >= 0 && cnt_j >= 0)
+                    groupby_consume_i64_sumcount_kernel<true, true><<<g, 256, 0, stream>>>(k, v, rows, d_keys.as<long long>(), cap, as, ac, ctr, limit, d_fail.as<uint32_t>());
+                else if (sum_j >= 0)
+                    groupby_consume_i64_sumcount_kernel<true, false><<<g, 256, 0, stream>>>(k, v, rows, d_keys.as<long long>(), cap, as, ac, ctr, limit, d_fail.as<uint32_t>());
+                else
+                    groupby_consume_i64_sumcount_kernel<false, true><<<g, 256, 0, stream>>>(k, v, rows, d_keys.as<long long>(), cap, as, ac, ctr, limit, d_fail.as<uint32_t>());
+            } else {
+                ConsumeArgs a{};
+                a.key_data = data[0]; a.key_valid = valid[0]; a.key_ctype = c_types[0]; a.dropna = dropna ? 1 : 0;
+                a.n_rows = rows; a.index_list = index_list; a.tkeys = d_keys.as<long long>(); a.cap = cap;
+                a.counters = ctr; a.group_limit = limit; a.fail_list = d_fail.as<uint32_t>(); a.n_ops = n_funcs;
+                for (int j = 0; j < n_funcs; j++) {
+                    const FuncSpec& f = funcs[j];
+                    a.ops[j].kind = f.kind; a.ops[j].in_ctype = f.in_ctype;
+                    a.ops[j].in_data = f.in_col >= 0 ? data[f.in_col] : nullptr;
+                    a.ops[j].in_valid = f.in_col >= 0 ? valid[f.in_col] : nullptr;
+                    a.ops[j].a0 = d_a0[j].p; a.ops[j].a1 = f.has_a1 ? d_a1[j].p : nullptr;
+                }
+                groupby_consume_kernel<<<grid_for(rows), 256, 0, stream>>>(a);
+            }
+            launches++;
+            B200_CUDA(cudaGetLastError());
+        };
+        launch(nullptr, n);
+        settle(n, could_fail, launch);
+        if (!could_fail) n_groups_bound += n;  // upper bound without a device round trip
+        else n_groups_bound = n_groups;
+        rows_consumed += n;
+    }
+
+    int64_t n_groups_bound = 0;  // upper bound on groups in the table known to the host
+    bool stage_recorded[2] = {false, false};
+
+    void consume(const b200_table* t) {
+        B200_REQUIRE(!build_done, "b200 groupby: consume after the build was finished");
+        B200_REQUIRE(t->n_cols == n_cols, "b200 groupby: batch has a different number of columns than the build schema");
+        B200_CUDA(cudaSetDevice(device));
+        int64_t n = t->n_rows;
+        std::vector<bool> used(n_cols, false);
+        used[0] = true;
+        for (auto& f : funcs) if (f.in_col >= 0) used[f.in_col] = true;
+        for (int c = 0; c < n_cols; c++) {
+            if (!used[c]) continue;
+            B200_REQUIRE(t->cols[c].c_type == c_types[c], "b200 groupby: batch column dtype differs from the build schema");
+            B200_REQUIRE(n == 0 || t->cols[c].data != nullptr, "b200 groupby: null data pointer");
+        }
+        if (t->device >= 0) {
+            B200_REQUIRE(t->device == device, "b200 groupby: batch lives on a different device than the state");
+            for (int64_t r0 = 0; r0 < n; r0 += CHUNK_ROWS) {
+                int64_t rows = std::min(CHUNK_ROWS, n - r0);
+                B200_REQUIRE(r0 % 8 == 0, "internal: chunk offset must be byte aligned for validity bitmaps");
+                std::vector<const void*> data(n_cols, nullptr);
+                std::vector<const uint8_t*> valid(n_cols, nullptr);
+                for (int c = 0; c < n_cols; c++) {
+                    if (!used[c]) continue;
+                    data[c] = (const char*)t->cols[c].data + r0 * ctype_size(c_types[c]);
+                    valid[c] = t->cols[c].validity ? t->cols[c].validity + r0 / 8 : nullptr;
+                }
+                consume_device_chunk(data, valid, rows);
+            }
+            return;
+        }
+        // host batch: pinned or pageable host memory, staged through two device buffers per column so the
+        // H2D copy of chunk c+1 overlaps the kernel of chunk c (replaces convertTableToGPU,
+        // bodo/pandas/physical/operator.cpp:293-380).
+        const int64_t HCHUNK = 1ll << 24;  // 16 Mi rows (128 MiB per 8-byte column)
+        if (!copy_stream) {
+            B200_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; b++) {
+                B200_CUDA(cudaEventCreateWithFlags(&stage_free[b], cudaEventDisableTiming));
+                B200_CUDA(cudaEventCreateWithFlags(&stage_ready[b], cudaEventDisableTiming));
+                stage[b].resize(2 * n_cols);
+            }
+        }
+        int64_t nchunks = (n + HCHUNK - 1) / HCHUNK;
+        for (int64_t ci = 0; ci < nchunks; ci++) {
+            int b = (int)(ci & 1);
+            int64_t r0 = ci * HCHUNK, rows = std::min(HCHUNK, n - r0);
+            if (stage_recorded[b]) B200_CUDA(cudaStreamWaitEvent(copy_stream, stage_free[b], 0));
+            std::vector<const void*> data(n_cols, nullptr);
+            std::vector<const uint8_t*> valid(n_cols, nullptr);
+            for (int c = 0; c < n_cols; c++) {
+                if (!used[c]) continue;
+                size_t isz = ctype_size(c_types[c]);
+                stage[b][2 * c].ensure((size_t)std::min(HCHUNK, n) * isz);
+                B200_CUDA(cudaMemcpyAsync(stage[b][2 * c].p, (const char*)t->cols[c].data + r0 * isz, rows * isz, cudaMemcpyHostToDevice, copy_stream));
+                data[c] = stage[b][2 * c].p;
+                if (t->cols[c].validity) {
+                    stage[b][2 * c + 1].ensure((size_t)(std::min(HCHUNK, n) + 7) / 8 + 8);
+                    B200_CUDA(cudaMemcpyAsync(stage[b][2 * c + 1].p, t->cols[c].validity + r0 / 8, (rows + 7) / 8, cudaMemcpyHostToDevice, copy_stream));
+                    valid[c] = stage[b][2 * c + 1].as<uint8_t>();
+                }
+            }
+            B200_CUDA(cudaEventRecord(stage_ready[b], copy_stream));
+            B200_CUDA(cudaStreamWaitEvent(stream, stage_ready[b], 0));
+            consume_device_chunk(data, valid, rows);
+            B200_CUDA(cudaEventRecord(stage_free[b], stream));
+            stage_recorded[b] = true;
+        }
+    }
+
+    // ---- finalize ----
+    void compact() {
+        read_counters();
+        n_groups_bound = n_groups;
+        int64_t max_out = n_groups + 2;
+        d_slot_of_out.ensure((size_t)max_out * 8);
+        B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 16, 0, 8, stream));
+        compact_slots_kernel<<<grid_for((int64_t)cap + 2), 256, 0, stream>>>(d_keys.as<long long>(), cap, (int)h_counters[3], (int)h_counters[4],
+                                                                                  d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>());
+        launches++;
+        B200_CUDA(cudaGetLastError());
+        read_counters();
+        n_out = h_counters[2];
+    }
+
+    int64_t finalize() {
+        if (finalized) return n_out;
+        B200_CUDA(cudaSetDevice(device));
+        compact();
+        EvalArgs e{};
+        e.tkeys = d_keys.as<long long>(); e.cap = cap; e.slot_of_out = d_slot_of_out.as<uint64_t>(); e.n_out = n_out;
+        e.key_ctype = c_types[0];
+        size_t words = (size_t)((n_out + 31) / 32 + 1);
+        d_out_keys.ensure((size_t)(n_out + 32) * ctype_size(c_types[0]));
+        e.out_keys = d_out_keys.p;
+        bool key_nullable = arr_types[0] == ARR_NULLABLE;
+        if (key_nullable) { d_out_key_valid.ensure(words * 4); e.out_key_valid = d_out_key_valid.as<uint32_t>(); }
+        e.n_ops = n_funcs;
+        for (int j = 0; j < n_funcs; j++) {
+            const FuncSpec& f = funcs[j];
+            d_out_data[j].ensure((size_t)(n_out + 32) * 8);
+            e.ops[j].kind = f.kind; e.ops[j].out_ctype = f.out_ctype; e.ops[j].a0 = d_a0[j].p;
+            e.ops[j].a1 = f.has_a1 ? d_a1[j].p : nullptr; e.ops[j].out_data = d_out_data[j].p;
+            if (f.out_arrtype == ARR_NULLABLE) { d_out_valid[j].ensure(words * 4); e.ops[j].out_valid = d_out_valid[j].as<uint32_t>(); }
+        }
+        if (n_out > 0) {
+            eval_output_kernel<<<grid_for(n_out), 256, 0, stream>>>(e);
+            launches++;
+            B200_CUDA(cudaGetLastError());
+        }
+        B200_CUDA(cudaStreamSynchronize(stream));
+        finalized = true;
+        out_cursor = 0;
+        return n_out;
+    }
+
+    int acc_count() const { int n = 0; for (auto& f : funcs) n += f.has_a1 ? 2 : 1; return n; }
+
+    // ---- exchange ----
+    int64_t shuffle_prepare(int64_t* send_counts) {
+        B200_CUDA(cudaSetDevice(device));
+        build_done = true;
+        compact();
+        d_dest_count.ensure((size_t)n_pes * 8);
+        B200_CUDA(cudaMemsetAsync(d_dest_count.p, 0, (size_t)n_pes * 8, stream));
+        PackArgs p = pack_args();
+        p.pass = 0; p.out = nullptr;
+        if (n_out > 0) { pack_partials_kernel<<<grid_for(n_out), 256, 0, stream>>>(p); launches++; B200_CUDA(cudaGetLastError()); }
+        h_dest_count.assign(n_pes, 0);
+        B200_CUDA(cudaMemcpyAsync(h_dest_count.data(), d_dest_count.p, (size_t)n_pes * 8, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA(cudaStreamSynchronize(stream));
+        for (int d = 0; d < n_pes; d++) send_counts[d] = h_dest_count[d];
+        packed_rows = n_out;
+        return (int64_t)(2 + acc_count()) * 8;
+    }
+    PackArgs pack_args() {
+        PackArgs p{};
+        p.tkeys = d_keys.as<long long>(); p.cap = cap; p.slot_of_out = d_slot_of_out.as<uint64_t>(); p.n_out = n_out; p.n_pes = n_pes;
+        int n = 0;
+        for (int j = 0; j < n_funcs; j++) {
+            p.acc[n++] = d_a0[j].as<unsigned long long>();
+            if (funcs[j].has_a1) p.acc[n++] = d_a1[j].as<unsigned long long>();
+        }
+        p.n_acc = n; p.row_words = 2 + n; p.dest_count = d_dest_count.as<long long>();
+        return p;
+    }
+    void shuffle_pack(void* send_buf) {
+        B200_CUDA(cudaSetDevice(device));
+        // exclusive scan of the per-destination counts -> running cursors
+        std::vector<long long> offs(n_pes, 0);
+        long long run = 0;
+        for (int d = 0; d < n_pes; d++) { offs[d] = run; run += h_dest_count[d]; }
+        B200_CUDA(cudaMemcpyAsync(d_dest_count.p, offs.data(), (size_t)n_pes * 8, cudaMemcpyHostToDevice, stream));
+        PackArgs p = pack_args();
+        p.pass = 1; p.out = (unsigned long long*)send_buf;
+        if (n_out > 0) { pack_partials_kernel<<<grid_for(n_out), 256, 0, stream>>>(p); launches++; B200_CUDA(cudaGetLastError()); }
+        // the table now only has to hold the groups this rank owns: clear it for the combine step
+        B200_CUDA(cudaStreamSynchronize(stream));  // offs is a stack buffer
+        fill(d_keys.p, cap + 2, (unsigned long long)EMPTY_KEY);
+        for (int j = 0; j < n_funcs; j++) { fill(d_a0[j].p, cap + 2, funcs[j].init0); if (funcs[j].has_a1) fill(d_a1[j].p, cap + 2, 0); }
+        B200_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(long long), stream));
+        n_groups = 0; n_groups_bound = 0;
+    }
+    void shuffle_combine(const void* recv, int64_t n_rows) {
+        B200_CUDA(cudaSetDevice(device));
+        if (n_rows == 0) return;
+        B200_REQUIRE(n_rows < (1ll << 32), "b200 groupby: too many partial rows in one combine call");
+        bool could_fail = (int64_t)(cap / 2) - n_groups_bound < n_rows;
+        if (could_fail) d_fail.ensure((size_t)n_rows * 4);
+        auto launch = [&](const uint32_t* index_list, int64_t rows) {
+            CombineArgs c{};
+            c.in = (const unsigned long long*)recv; c.n_rows = rows; c.row_words = 2 + acc_count();
+            c.tkeys = d_keys.as<long long>(); c.cap = cap; c.counters = d_counters.as<long long>(); c.group_limit = (long long)(cap / 2);
+            c.fail_list = d_fail.as<uint32_t>(); c.index_list = index_list; c.n_ops = n_funcs;
+            for (int j = 0; j < n_funcs; j++) { c.kinds[j] = funcs[j].kind; c.a0[j] = d_a0[j].p; c.a1[j] = funcs[j].has_a1 ? d_a1[j].p : nullptr; }
+            combine_partials_kernel<<<grid_for(rows), 256, 0, stream>>>(c);
+            launches++;
+            B200_CUDA(cudaGetLastError());
+        };
+        launch(nullptr, n_rows);
+        settle(n_rows, could_fail, launch);
+        if (!could_fail) n_groups_bound += n_rows; else n_groups_bound = n_groups;
+    }
+
+    int produce(b200_table* out, int32_t* out_is_last, bool produce_output) {
+        if (!finalized) finalize();
+        int64_t bs = output_batch_size > 0 ? output_batch_size : n_out;
+        if (bs % 32 != 0 && bs < n_out) bs = (bs + 31) & ~31ll;  // validity bitmaps are sliced at word granularity
+        int64_t rows = produce_output ? std::min(bs, n_out - out_cursor) : 0;
+        B200_REQUIRE(out->cols != nullptr, "b200 groupby: out->cols must point to n_keys + n_funcs descriptors");
+        out->n_rows = rows; out->n_cols = 1 + n_funcs; out->device = device;
+        int64_t off = out_cursor;
+        b200_column& k = out->cols[0];
+        k.data = (char*)d_out_keys.p + off * ctype_size(c_types[0]);
+        k.validity = arr_types[0] == ARR_NULLABLE ? d_out_key_valid.as<uint8_t>() + off / 8 : nullptr;
+        k.length = rows; k.c_type = c_types[0]; k.arr_type = arr_types[0];
+        for (int j = 0; j < n_funcs; j++) {
+            b200_column& c = out->cols[1 + j];
+            c.data = (char*)d_out_data[j].p + off * ctype_size(funcs[j].out_ctype);
+            c.validity = funcs[j].out_arrtype == ARR_NULLABLE ? d_out_valid[j].as<uint8_t>() + off / 8 : nullptr;
+            c.length = rows; c.c_type = funcs[j].out_ctype; c.arr_type = funcs[j].out_arrtype;
+        }
+        out_cursor += rows;
+        *out_is_last = out_cursor >= n_out ? 1 : 0;
+        return 0;
+    }
+};
+
+}  // namespace b200
+
+using b200::GroupbyState;
+
+#define B200_TRY try {
+#define B200_CATCH(retval)                              \
+    }                                                   \
+    catch (const std::exception& e) {                   \
+        b200::set_last_error(e.what());                 \
+        return retval;                                  \
+    }
+
+extern "C" {
+
+void* b200_groupby_state_init(int64_t operator_id, const int8_t* build_arr_c_types, const int8_t* build_arr_array_types,
+                              int32_t n_build_arrs, const int32_t* ftypes, const int32_t* f_in_offsets,
+                              const int32_t* f_in_cols, int32_t n_funcs, uint64_t n_keys, int64_t output_batch_size,
+                              int32_t parallel, int32_t pandas_drop_na, int32_t device, int32_t n_pes, int32_t myrank,
+                              int64_t expected_groups, void* stream) {
+    (void)operator_id;
+    B200_TRY
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw b200::Error("b200 groupby: no CUDA device available (this path has no CPU fallback)");
+    B200_REQUIRE(device >= 0 && device < ndev, "b200 groupby: bad device ordinal");
+    return new GroupbyState(build_arr_c_types, build_arr_array_types, n_build_arrs, ftypes, f_in_offsets, f_in_cols, n_funcs,
+                            n_keys, output_batch_size, parallel != 0, pandas_drop_na != 0, device, n_pes, myrank,
+                            expected_groups, (cudaStream_t)stream);
+    B200_CATCH(nullptr)
+}
+
+int b200_groupby_build_consume_batch(void* state, const b200_table* in_table, int32_t is_last, int32_t is_final_pipeline,
+                                     int32_t* request_input) {
+    (void)is_final_pipeline;
+    B200_TRY
+    B200_REQUIRE(state && in_table, "b200 groupby: null state or table");
+    auto* s = (GroupbyState*)state;
+    s->consume(in_table);
+    if (request_input) *request_input = 1;
+    if (is_last && !s->parallel) s->build_done = true;
+    return is_last ? 1 : 0;
+    B200_CATCH(-1)
+}
+
+int64_t b200_groupby_shuffle_prepare(void* state, int64_t* send_row_counts) {
+    B200_TRY
+    return ((GroupbyState*)state)->shuffle_prepare(send_row_counts);
+    B200_CATCH(-1)
+}
+int64_t b200_groupby_shuffle_send_bytes(void* state) {
+    auto* s = (GroupbyState*)state;
+    return s->packed_rows * (int64_t)(2 + s->acc_count()) * 8;
+}
+int b200_groupby_shuffle_pack(void* state, void* send_buf) {
+    B200_TRY
+    ((GroupbyState*)state)->shuffle_pack(send_buf);
+    return 0;
+    B200_CATCH(-1)
+}
+int b200_groupby_shuffle_combine(void* state, const void* recv_buf, int64_t n_recv_rows) {
+    B200_TRY
+    ((GroupbyState*)state)->shuffle_combine(recv_buf, n_recv_rows);
+    return 0;
+    B200_CATCH(-1)
+}
+int64_t b200_groupby_finalize(void* state) {
+    B200_TRY
+    return ((GroupbyState*)state)->finalize();
+    B200_CATCH(-1)
+}
+int b200_groupby_produce_output_batch(void* state, b200_table* out, int32_t* out_is_last, int32_t produce_output) {
+    B200_TRY
+    B200_REQUIRE(state && out && out_is_last, "b200 groupby: null argument");
+    return ((GroupbyState*)state)->produce(out, out_is_last, produce_output != 0);
+    B200_CATCH(-1)
+}
+void b200_delete_groupby_state(void* state) { delete (GroupbyState*)state; }
+
+int64_t b200_groupby_get_metric(void* state, int32_t which) {
+    auto* s = (GroupbyState*)state;
+    switch (which) {
+        case 0: return s->finalized ? s->n_out : s->n_groups;
+        case 1: return (int64_t)s->cap;
+        case 2: return s->rows_consumed;
+        case 3: return s->rebuilds;
+        case 4: return s->launches;
+        case 5: return s->fail_rows;
+        default: return -1;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// misc.cu — error reporting, runtime probes, raw memory helpers and the synthetic-table generator.
+#include "common.cuh"
+
+namespace b200 {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+// key = mix64(row ^ seed-derived salt) % n_groups ; val = (mix64(...) % 1000) - 500 (INT64) or u01 (FLOAT64).
+// Same arithmetic as oracle_synth_fill (oracle/bodo_oracle.c) and bodo_b200/synth.py.
+__global__ void synth_fill_kernel(long long* keys, void* vals, int64_t row_start, int64_t n, uint64_t n_groups, uint64_t seed,
+                                  int val_ctype) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint64_t salt_k = seed * 0x9e3779b97f4a7c15ULL, salt_v = (seed + 1) * 0xd1b54a32d192ed03ULL;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t r = (uint64_t)(row_start + i);
+        if (keys) keys[i] = (long long)(mix64(r ^ salt_k) % n_groups);
+        if (vals) {
+            uint64_t m = mix64(r ^ salt_v);
+            if (val_ctype == CT_FLOAT64) ((double*)vals)[i] = (double)(m >> 11) * (1.0 / 9007199254740992.0);
+            else ((long long*)vals)[i] = (long long)(m % 1000) - 500;
+        }
+    }
+}
+}  // namespace b200
+
+extern "C" {
+
+const char* b200_last_error(void) { return b200::g_last_error.c_str(); }
+int b200_abi_version(void) { return 1; }
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void* b200_device_malloc(int32_t device, int64_t nbytes) {
+    try {
+        B200_CUDA(cudaSetDevice(device));
+        void* p = nullptr;
+        B200_CUDA(cudaMalloc(&p, (size_t)(nbytes > 0 ? nbytes : 8)));
+        return p;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return nullptr; }
+}
+void b200_device_free(int32_t device, void* p) {
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaFree(p);
+}
+int b200_memcpy_d2h(void* dst_host, const void* src_dev, int64_t nbytes, void* stream) {
+    try {
+        if (nbytes <= 0) return 0;
+        B200_CUDA(cudaMemcpyAsync(dst_host, src_dev, (size_t)nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        B200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+int b200_memcpy_h2d(void* dst_dev, const void* src_host, int64_t nbytes, void* stream) {
+    try {
+        if (nbytes <= 0) return 0;
+        B200_CUDA(cudaMemcpyAsync(dst_dev, src_host, (size_t)nbytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        B200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+int b200_stream_synchronize(void* stream) {
+    try { B200_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
+    catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+int b200_synth_fill(void* key_out, void* val_out, int64_t row_start, int64_t n_rows, int64_t n_groups, uint64_t seed,
+                    int32_t val_c_type, void* stream) {
+    try {
+        B200_REQUIRE(n_groups > 0, "b200_synth_fill: n_groups must be positive");
+        B200_REQUIRE(val_c_type == b200::CT_INT64 || val_c_type == b200::CT_FLOAT64, "b200_synth_fill: value type must be INT64 or FLOAT64");
+        if (n_rows <= 0) return 0;
+        int dev = 0;
+        B200_CUDA(cudaGetDevice(&dev));
+        int grid = b200::num_sms(dev) * 8;
+        b200::synth_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((long long*)key_out, val_out, row_start, n_rows, (uint64_t)n_groups, seed, val_c_type);
+        B200_CUDA(cudaGetLastError());
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+}  // extern "C"

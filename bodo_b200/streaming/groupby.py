@@ -1,0 +1,208 @@
+"""Streaming groupby operator API — the host-side mirror of bodo/libs/streaming/groupby.py.
+
+Same four verbs, same argument meaning and the same calling protocol as the reference
+(init_groupby_state :702-715, groupby_build_consume_batch :1295-1395, groupby_produce_output_batch
+:1502-1600, delete_groupby_state), so the reference's streaming test loops
+(bodo/tests/test_streaming/test_groupby.py:51-81) run unchanged against this module.  The work happens in
+libbodo_b200.so (CUDA, sm_100a); there is no CPU implementation behind these calls.
+
+Differences: the reference types the state at Numba compile time; here the build-table schema is taken
+from the first consumed batch.  With parallel=True the state is one shard of a torch.distributed process
+group (one process per GPU): the last consume call runs the hash-partition exchange that replaces the
+reference's MPI shuffle (streaming/_shuffle.cpp:687-804).
+"""
+
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+
+from .. import _lib
+from .._lib import ffi
+from ..table import CTable, Table, table_from_ctable
+
+# names must match supported_agg_funcs positions / Bodo_FTypes (groupby/_groupby_ftypes.h:17-110)
+FTYPES = {"size": 4, "sum": 6, "count": 7, "mean": 14, "min": 15, "max": 16}
+
+
+class GroupbyState:
+    """Python handle of the C GroupbyState (created lazily at the first consume call)."""
+
+    def __init__(self, operator_id, key_inds, fnames, f_in_offsets, f_in_cols, parallel, dropna, output_batch_size,
+                 expected_groups, device, stream, process_group):
+        self.operator_id = int(operator_id)
+        self.key_inds = tuple(int(k) for k in key_inds)
+        self.fnames = tuple(fnames)
+        for f in self.fnames:
+            if f not in FTYPES:
+                raise _lib.B200Error(
+                    f"Streaming Groupby: unsupported aggregate function '{f}' (supported: {sorted(FTYPES)})")
+        self.f_in_offsets = tuple(int(x) for x in f_in_offsets)
+        self.f_in_cols = tuple(int(x) for x in f_in_cols)
+        if len(self.f_in_offsets) != len(self.fnames) + 1:
+            raise _lib.B200Error("Streaming Groupby: f_in_offsets must have len(fnames) + 1 entries")
+        self.parallel = bool(parallel)
+        self.dropna = bool(dropna)
+        self.output_batch_size = int(output_batch_size)
+        self.expected_groups = int(expected_groups)
+        self.device = device
+        self.stream = int(stream)
+        self.process_group = process_group
+        self.handle = None
+        self.build_indices = None  # physical column order: keys first (as the reference's build_indices)
+        self.out_names = None
+        self._out_cols = None
+        self._out_tab = None
+        self.exchanged = False
+
+    # -- lazy C state creation once the input schema is known
+    def _ensure(self, table: Table):
+        if self.handle is not None:
+            return
+        L = _lib.lib()
+        _lib.require_gpu()
+        n = table.n_cols
+        others = [i for i in range(n) if i not in self.key_inds]
+        self.build_indices = list(self.key_inds) + others
+        remap = {logical: phys for phys, logical in enumerate(self.build_indices)}
+        phys_f_in_cols = [remap[c] for c in self.f_in_cols]
+        cols = [table.columns[i] for i in self.build_indices]
+        c_types = ffi.new("int8_t[]", [c.c_type for c in cols])
+        a_types = ffi.new("int8_t[]", [c.arr_type for c in cols])
+        ftypes = ffi.new("int32_t[]", [FTYPES[f] for f in self.fnames] or [0])
+        offs = ffi.new("int32_t[]", list(self.f_in_offsets))
+        fcols = ffi.new("int32_t[]", phys_f_in_cols or [0])
+        if self.device is None:
+            self.device = table.device if table.device >= 0 else _current_device()
+        n_pes, rank = 1, 0
+        if self.parallel:
+            import torch.distributed as dist
+
+            n_pes, rank = dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+        self.n_pes, self.rank = n_pes, rank
+        h = L.b200_groupby_state_init(self.operator_id, c_types, a_types, len(cols), ftypes, offs, fcols,
+                                      len(self.fnames), len(self.key_inds), self.output_batch_size,
+                                      int(self.parallel and n_pes > 1), int(self.dropna), self.device, n_pes, rank,
+                                      self.expected_groups, ffi.cast("void*", self.stream))
+        self.handle = _lib.check_ptr(h, "init_groupby_state")
+        key_names = [table.names[i] for i in self.key_inds]
+        fn_names = []
+        for j, f in enumerate(self.fnames):
+            lo, hi = self.f_in_offsets[j], self.f_in_offsets[j + 1]
+            fn_names.append(table.names[self.f_in_cols[lo]] if hi > lo else f)
+        # output names must be unique: a column aggregated more than once gets a _<func> suffix
+        seen = set(key_names)
+        uniq = []
+        for f, nm in zip(self.fnames, fn_names):
+            cand, k = nm, 0
+            while cand in seen:
+                cand = f"{nm}_{f}" if k == 0 else f"{nm}_{f}{k}"
+                k += 1
+            seen.add(cand)
+            uniq.append(cand)
+        self.out_names = key_names + uniq
+
+    def _exchange(self):
+        """Hash-partition exchange of the partial aggregates (one all-to-all-v), then combine."""
+        import torch
+        import torch.distributed as dist
+
+        L = _lib.lib()
+        h = self.handle
+        counts = ffi.new("int64_t[]", self.n_pes)
+        row_bytes = _lib.check(L.b200_groupby_shuffle_prepare(h, counts), "groupby shuffle prepare")
+        send_counts = [int(counts[i]) for i in range(self.n_pes)]
+        dev = torch.device("cuda", self.device)
+        words = row_bytes // 8
+        send = torch.empty((max(sum(send_counts), 1), words), dtype=torch.int64, device=dev)
+        _lib.check(L.b200_groupby_shuffle_pack(h, ffi.cast("void*", send.data_ptr())), "groupby shuffle pack")
+        sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc, group=self.process_group)  # mpi_comm_info's MPI_Alltoall (_shuffle.cpp:210-213)
+        recv_counts = [int(x) for x in rc.cpu().tolist()]
+        recv = torch.empty((max(sum(recv_counts), 1), words), dtype=torch.int64, device=dev)
+        # b200_groupby_shuffle_pack returns with its stream drained, so `send` is complete here
+        dist.all_to_all_single(recv[: sum(recv_counts)], send[: sum(send_counts)], output_split_sizes=recv_counts,
+                               input_split_sizes=send_counts, group=self.process_group)
+        torch.cuda.current_stream(dev).synchronize()
+        _lib.check(L.b200_groupby_shuffle_combine(h, ffi.cast("void*", recv.data_ptr()), sum(recv_counts)),
+                   "groupby shuffle combine")
+        L.b200_stream_synchronize(ffi.cast("void*", self.stream))
+        self.exchanged = True
+        self.shuffle_bytes = sum(send_counts) * row_bytes
+
+
+def _current_device() -> int:
+    import torch
+
+    return torch.cuda.current_device()
+
+
+def init_groupby_state(operator_id, key_inds, fnames, f_in_offsets, f_in_cols, mrnf_sort_col_inds=None,
+                       mrnf_sort_col_asc=None, mrnf_sort_col_na=None, mrnf_col_inds_keep=None, op_pool_size_bytes=-1,
+                       parallel=False, *, dropna=True, output_batch_size=32768, expected_groups=0, device=None,
+                       stream=0, process_group=None) -> GroupbyState:
+    """Mirror of bodo.libs.streaming.groupby.init_groupby_state (groupby.py:702-715).
+
+    key_inds / f_in_cols index the logical input table; fnames are names from supported_agg_funcs.
+    The MRNF arguments must be None (min_row_number_filter is out of scope) and op_pool_size_bytes is
+    ignored (the table is sized in HBM, there is no host operator pool).
+    Keyword-only extras: dropna (pandas_drop_na of the C++ ctor), output_batch_size, expected_groups
+    (sizing hint), device, stream (cudaStream_t as int), process_group (torch.distributed).
+    """
+    if any(x is not None for x in (mrnf_sort_col_inds, mrnf_sort_col_asc, mrnf_sort_col_na, mrnf_col_inds_keep)):
+        raise _lib.B200Error("Streaming Groupby: min_row_number_filter is not supported by bodo_b200")
+    key_inds = getattr(key_inds, "meta", key_inds)
+    fnames = getattr(fnames, "meta", fnames)
+    f_in_offsets = getattr(f_in_offsets, "meta", f_in_offsets)
+    f_in_cols = getattr(f_in_cols, "meta", f_in_cols)
+    return GroupbyState(operator_id, key_inds, fnames, f_in_offsets, f_in_cols, parallel, dropna, output_batch_size,
+                        expected_groups, device, stream, process_group)
+
+
+def groupby_build_consume_batch(groupby_state: GroupbyState, table: Table, is_last: bool, is_final_pipeline: bool = True):
+    """Mirror of groupby_build_consume_batch (groupby.py:1295-1395): returns (is_last, request_input).
+
+    Collective when the state is parallel: every rank must pass is_last=True in the same call (ranks that
+    ran out of input keep calling with empty batches, as in the reference's pipeline loop,
+    bodo/pandas/_pipeline.cpp:453-457)."""
+    st = groupby_state
+    st._ensure(table)
+    L = _lib.lib()
+    phys = table.select(st.build_indices)
+    ct = CTable(phys)
+    req = ffi.new("int32_t*")
+    rc = _lib.check(L.b200_groupby_build_consume_batch(st.handle, ct.ptr, int(bool(is_last)), int(bool(is_final_pipeline)), req),
+                    "groupby_build_consume_batch")
+    if is_last and st.parallel and st.n_pes > 1 and not st.exchanged:
+        st._exchange()
+    return bool(rc), bool(req[0])
+
+
+def groupby_produce_output_batch(groupby_state: GroupbyState, produce_output: bool = True):
+    """Mirror of groupby_produce_output_batch (groupby.py:1502-1600): returns (out_table, is_last).
+    The returned Table wraps library-owned device columns that stay valid until the next produce call."""
+    st = groupby_state
+    if st.handle is None:
+        raise _lib.B200Error("groupby_produce_output_batch called before any build batch was consumed")
+    L = _lib.lib()
+    ncols = len(st.key_inds) + len(st.fnames)
+    st._out_cols = ffi.new("b200_column[]", ncols)
+    st._out_tab = ffi.new("b200_table*")
+    st._out_tab.cols = st._out_cols
+    last = ffi.new("int32_t*")
+    _lib.check(L.b200_groupby_produce_output_batch(st.handle, st._out_tab, last, int(bool(produce_output))),
+               "groupby_produce_output_batch")
+    out = table_from_ctable(st._out_tab, ncols, st.out_names, owner=st)
+    return out, bool(last[0])
+
+
+def delete_groupby_state(groupby_state: GroupbyState) -> None:
+    if groupby_state.handle is not None:
+        _lib.lib().b200_delete_groupby_state(groupby_state.handle)
+        groupby_state.handle = None
+
+
+def get_metric(groupby_state: GroupbyState, which: int) -> int:
+    return int(_lib.lib().b200_groupby_get_metric(groupby_state.handle, which))

@@ -1,0 +1,173 @@
+/*
+ * bodo_b200.h — C ABI of libbodo_b200.so: the B200-native replacement for Bodo's streaming
+ * hash groupby / hash join / row->rank shuffle hot path.
+ *
+ * Every entry point mirrors one reference FFI symbol (cited per function, paths relative to the
+ * reference checkout). Differences from the reference ABI, all deliberate:
+ *   - tables cross the boundary as `b200_table` (plain column descriptors: data pointer, Arrow
+ *     validity bitmap, Bodo_CTypes / bodo_array_type codes) instead of `table_info*`;
+ *   - errors are reported by return code + b200_last_error() instead of the CPython error
+ *     indicator (reference: PyErr_SetString, bodo/libs/streaming/_groupby.cpp:4669-4675);
+ *   - input tables are BORROWED for the duration of the call (the reference steals them).
+ * No torch / CUDA types appear in any signature: streams are passed as void* (cudaStream_t).
+ *
+ * This header is also parsed by cffi (bodo_b200/_lib.py): keep it plain C89 declarations;
+ * lines starting with '#' are stripped before parsing.
+ */
+#ifndef BODO_B200_H
+#define BODO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- data model (reference: bodo/libs/_bodo_common.h:331-359 Bodo_CTypes, :515-532 bodo_array_type,
+ *      :927 array_info, :1819 table_info) ---- */
+
+/* b200_column.c_type uses Bodo_CTypes codes: INT8=0 UINT8=1 INT32=2 UINT32=3 INT64=4 FLOAT32=5
+ * FLOAT64=6 UINT64=7 INT16=8 UINT16=9 _BOOL=11 DATE=13 DATETIME=15 TIMEDELTA=16.
+ * b200_column.arr_type uses bodo_array_type codes: NUMPY=0, NULLABLE_INT_BOOL=2. */
+typedef struct b200_column {
+    void* data;        /* contiguous values, length * itemsize bytes (host or device, see b200_table.device) */
+    uint8_t* validity; /* Arrow validity bitmap (bit i%8 of byte i/8, 1 = valid) or NULL = all valid */
+    int64_t length;
+    int32_t c_type;
+    int32_t arr_type;
+} b200_column;
+
+typedef struct b200_table {
+    int64_t n_rows;
+    int32_t n_cols;
+    int32_t device; /* -1: pointers are host memory; >= 0: CUDA device ordinal owning the pointers */
+    b200_column* cols;
+} b200_table;
+
+/* Last error message of the calling thread ("" if none). Every int-returning entry point returns
+ * a negative value on error; pointer-returning ones return NULL. */
+const char* b200_last_error(void);
+
+/* Library/runtime probes (used by tests and __graft_entry__). b200_device_count() returns 0 without
+ * a GPU and never raises; all compute entry points fail with an error instead of falling back. */
+int b200_abi_version(void);
+int b200_device_count(void);
+
+/* ---- streaming hash groupby (reference door 1: bodo/libs/streaming/_groupby.cpp) ---- */
+
+/* groupby_state_init_py_entry (_groupby.cpp:4917-4970). Keys are the first n_keys columns of every
+ * build batch; ftypes are Bodo_FTypes (groupby/_groupby_ftypes.h:17-110: size=4 sum=6 count=7 mean=14
+ * min=15 max=16); f_in_offsets/f_in_cols is the CSR map function -> physical input column
+ * (streaming/_groupby.h:1059-1070). Arguments of the reference that only concern window functions,
+ * MRNF, sort keys and the host operator pool are dropped. `pandas_drop_na`: drop rows with NA keys
+ * (filter_na_keys, _groupby.cpp:4278-4309). `parallel`: state is one shard of n_pes; ownership
+ * is hash_to_rank(key) (bodo/libs/_shuffle.h:5-7). `expected_groups` is a sizing hint (0 = unknown).
+ * `stream` is a cudaStream_t all work is enqueued on (NULL = legacy default stream). */
+void* b200_groupby_state_init(int64_t operator_id, const int8_t* build_arr_c_types,
+                              const int8_t* build_arr_array_types, int32_t n_build_arrs,
+                              const int32_t* ftypes, const int32_t* f_in_offsets,
+                              const int32_t* f_in_cols, int32_t n_funcs, uint64_t n_keys,
+                              int64_t output_batch_size, int32_t parallel, int32_t pandas_drop_na,
+                              int32_t device, int32_t n_pes, int32_t myrank,
+                              int64_t expected_groups, void* stream);
+
+/* groupby_build_consume_batch_py_entry (_groupby.cpp:4663-4676). Returns 1 when the build is globally
+ * finished (is_last was passed), 0 otherwise, <0 on error. *request_input is always set to 1 (the GPU
+ * state sizes its table up front and never back-pressures). */
+int b200_groupby_build_consume_batch(void* state, const b200_table* in_table, int32_t is_last,
+                                     int32_t is_final_pipeline, int32_t* request_input);
+
+/* Multi-rank exchange step, replacing GroupbyIncrementalShuffleState (streaming/_groupby.cpp:1558-1873)
+ * + shuffle_issend/irecv (streaming/_shuffle.cpp:567-652): after the last local batch,
+ *   1. b200_groupby_shuffle_prepare: compacts the local partial aggregates and radix-partitions them by
+ *      hash_to_rank into one packed send buffer (layout: see DESIGN.md "partial-aggregate wire format");
+ *      writes n_pes send row counts (host) and returns the packed row width in bytes;
+ *   2. the host exchanges counts and bytes (ncclSend/Recv all-to-all-v; torch.distributed plumbing);
+ *   3. b200_groupby_shuffle_combine merges the received partial rows (combine functions of
+ *      groupby/_groupby_update.cpp:41-57: count/size/mean -> sum, min -> min, max -> max).
+ * send_buf must hold b200_groupby_shuffle_send_bytes(state) bytes on the state's device. */
+int64_t b200_groupby_shuffle_prepare(void* state, int64_t* send_row_counts);
+int64_t b200_groupby_shuffle_send_bytes(void* state);
+int b200_groupby_shuffle_pack(void* state, void* send_buf);
+int b200_groupby_shuffle_combine(void* state, const void* recv_buf, int64_t n_recv_rows);
+
+/* FinalizeBuild (_groupby.cpp:4062-4256): evaluates the output columns (mean_eval etc.). Called
+ * implicitly by the first produce call; exposed so the exchange step can be timed separately.
+ * Returns the number of output rows (groups owned by this shard). */
+int64_t b200_groupby_finalize(void* state);
+
+/* groupby_produce_output_batch_py_entry (_groupby.cpp:4772-4783). Fills `out` (caller provides
+ * out->cols with room for n_keys + n_funcs descriptors) with pointers to library-owned device
+ * columns holding the next <= output_batch_size groups; they stay valid until the next produce call
+ * or delete. Sets *out_is_last. Output order of groups is unspecified (as in the reference). */
+int b200_groupby_produce_output_batch(void* state, b200_table* out, int32_t* out_is_last,
+                                      int32_t produce_output);
+
+/* delete_groupby_state (_groupby.cpp:5246). */
+void b200_delete_groupby_state(void* state);
+
+/* Metrics (subset of GroupbyMetrics, streaming/_groupby.h:106-223): 0 n_groups, 1 table capacity,
+ * 2 rows consumed, 3 table rebuilds, 4 kernel launches so far, 5 rows taken by the fallback list. */
+int64_t b200_groupby_get_metric(void* state, int32_t which);
+
+/* ---- streaming hash join (reference: bodo/libs/streaming/_join.cpp) ---- */
+
+/* join_state_init_py_entry (_join.cpp:4087-4136). Inner equi-join on the first n_keys (=1) columns;
+ * build_table_outer / probe_table_outer select right/left/full-outer semantics. */
+void* b200_join_state_init(int64_t operator_id, const int8_t* build_arr_c_types,
+                           const int8_t* build_arr_array_types, int32_t n_build_arrs,
+                           const int8_t* probe_arr_c_types, const int8_t* probe_arr_array_types,
+                           int32_t n_probe_arrs, uint64_t n_keys, int32_t build_table_outer,
+                           int32_t probe_table_outer, int64_t output_batch_size, int32_t device,
+                           int64_t expected_build_rows, void* stream);
+
+/* join_build_consume_batch_py_entry (_join.cpp:4149-4185): appends a build batch; on is_last builds the
+ * hash table + CSR groups (JoinPartition::BuildHashTable / FinalizeGroups, _join.cpp:381-512). */
+int b200_join_build_consume_batch(void* state, const b200_table* in_table, int32_t is_last,
+                                  int32_t* request_input);
+
+/* join_probe_consume_batch_py_entry (_join.cpp:4205-4260): probes one batch and materialises the joined
+ * rows (kept build columns then kept probe columns, reference order: build table first) into
+ * library-owned device columns described by `out` (valid until the next probe call). *total_rows
+ * receives the number of output rows of this call. */
+int b200_join_probe_consume_batch(void* state, const b200_table* in_table,
+                                  const uint64_t* kept_build_cols, int64_t n_kept_build,
+                                  const uint64_t* kept_probe_cols, int64_t n_kept_probe,
+                                  b200_table* out, int64_t* total_rows, int32_t is_last,
+                                  int32_t* out_is_last);
+
+/* delete_join_state (_join.cpp:4429). */
+void b200_delete_join_state(void* state);
+int64_t b200_join_get_metric(void* state, int32_t which);
+
+/* ---- row -> rank shuffle (reference: bodo/libs/_shuffle.cpp) ---- */
+
+/* hash_keys_table(SEED_HASH_PARTITION) + hash_to_rank (bodo/libs/_array_hash.cpp:76-109,
+ * _shuffle.h:5-7): dest[i] = (uint32)XXH3_64bits_withSeed(&key[i], 8, 0xb0d01289) % n_pes. Writes
+ * per-row destinations (device int32) — exposed for placement-parity tests. */
+int b200_hash_to_rank(const b200_table* in_table, int32_t n_pes, int32_t* dest_out, void* stream);
+
+/* mpi_comm_info::set_send_count + fill_send_array (bodo/libs/_shuffle.cpp:94-163,345-368,477+) as one
+ * radix-partition pass: histogram of destinations, exclusive scan, stable scatter of every column
+ * into per-destination contiguous segments. `out` columns (device, same schema/length as the input,
+ * provided by the caller) receive the rows grouped by destination; send_counts (host, n_pes) the
+ * rows per destination. Validity bitmaps are re-packed per destination segment at byte granularity
+ * (segment d starts at byte offset of a fresh bitmap: see DESIGN.md). */
+int b200_shuffle_partition(const b200_table* in_table, int64_t n_keys, int32_t n_pes,
+                           b200_table* out, int64_t* send_counts, void* stream);
+
+/* ---- helpers for host code that does not link CUDA ---- */
+void* b200_device_malloc(int32_t device, int64_t nbytes);
+void b200_device_free(int32_t device, void* p);
+int b200_memcpy_d2h(void* dst_host, const void* src_dev, int64_t nbytes, void* stream);
+int b200_memcpy_h2d(void* dst_dev, const void* src_host, int64_t nbytes, void* stream);
+int b200_stream_synchronize(void* stream);
+
+/* Synthetic table generator used by bench.py (counter-based, seeded; mirrored by the numpy generator
+ * in bodo_b200/synth.py so the oracle sees the same rows): key = mix64(seed_k, row) % n_groups,
+ * val = (int64)(mix64(seed_v, row) % 1000) - 500 (INT64) or u01 (FLOAT64). */
+int b200_synth_fill(void* key_out, void* val_out, int64_t row_start, int64_t n_rows, int64_t n_groups,
+                    uint64_t seed, int32_t val_c_type, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BODO_B200_H */

@@ -1,0 +1,138 @@
+"""GPU parity tests for the streaming hash groupby (call through the C ABI; compare with the CPU oracle
+and with pandas, the reference's own oracle).  Bar: integer aggregates bit-exact; float aggregates within
+rtol=1e-5 / atol=1e-8 (bodo/tests/utils.py:179-180)."""
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from bodo_b200.table import Table
+from tests.helpers import (assert_frames_equal, oracle_groupby_frame, positional, stream_groupby)
+
+pytestmark = pytest.mark.gpu
+
+
+def _basic_df(use_np_data):
+    # test_groupby_basic fixture (bodo/tests/test_streaming/test_groupby.py:83-96)
+    groups = [1, 2, 1, 1, 2, 0, 1, 2] * 100
+    data = [1, 3, 5, 11, 1, 3, 5, 3] * 100
+    return pd.DataFrame({"A": groups, "B": np.array(data, dtype=np.int32) if use_np_data else data})
+
+
+@pytest.mark.parametrize("func_name", ["sum", "mean", "count", "min", "max", "size"])
+@pytest.mark.parametrize("use_np_data", [True, False])
+@pytest.mark.parametrize("to_device", [False, True])
+def test_groupby_basic(gpu_lib, oracle, func_name, use_np_data, to_device):
+    df = _basic_df(use_np_data)
+    t = Table.from_pandas(df)
+    got = stream_groupby(t, (0,), (func_name,), (0, 1), (1,), batch_size=3 if not to_device else 96, to_device=to_device)
+    exp = df.groupby("A", as_index=False).agg(func_name) if func_name != "size" else df.groupby("A", as_index=False).size()
+    assert_frames_equal(positional(got), positional(exp))
+    assert_frames_equal(positional(got), oracle_groupby_frame(oracle, t, 0, [func_name], [1], batch_size=3))
+
+
+def test_groupby_key_reorder(gpu_lib):
+    # key is not the first column (bodo/tests/test_streaming/test_groupby.py:180-245)
+    df = pd.DataFrame({"B": np.arange(800, dtype=np.int64) * 3, "A": [1, 2, 1, 1, 2, 0, 1, 2] * 100, "C": np.arange(800, dtype=np.float64)})
+    t = Table.from_pandas(df)
+    got = stream_groupby(t, (1,), ("sum", "mean"), (0, 1, 2), (0, 2), batch_size=7)
+    exp = df.groupby("A", as_index=False).agg(B=("B", "sum"), C=("C", "mean"))
+    assert_frames_equal(positional(got), positional(exp))
+
+
+def test_quickstart_example(gpu_lib):
+    # README / test_quickstart_docs.py:29-63 shape: 2000 rows % 30 groups, max
+    df = pd.DataFrame({"A": np.arange(2000) % 30, "B": np.arange(2000)})
+    got = stream_groupby(Table.from_pandas(df), (0,), ("max",), (0, 1), (1,), batch_size=512)
+    assert_frames_equal(positional(got), positional(df.groupby("A", as_index=False).B.max()))
+
+
+@pytest.mark.parametrize("dropna", [True, False])
+def test_nullable_keys_and_values(gpu_lib, oracle, dropna):
+    # test_series_groupby / test_dataframe_groupby fixtures (bodo/tests/test_df_lib/test_end_to_end.py:1606-1660)
+    df = pd.DataFrame({
+        "A": pd.array([1, 2, None, 2147483647, 1, None, 2, 1] * 40, dtype="Int64"),
+        "B": pd.array([1.5, None, 3.0, 4.0, None, 6.0, 7.5, 8.0] * 40, dtype="Float64"),
+        "C": pd.array([1, 2, 3, None, 5, 6, None, 8] * 40, dtype="Int32"),
+    })
+    t = Table.from_pandas(df)
+    fn = ("sum", "mean", "count", "min", "max", "sum", "count", "min", "max", "size")
+    offs = tuple(range(len(fn))) + (len(fn) - 1,)
+    cols = (1, 1, 1, 1, 1, 2, 2, 2, 2)
+    got = stream_groupby(t, (0,), fn, offs, cols, batch_size=64, dropna=dropna)
+    exp = oracle_groupby_frame(oracle, t, 0, list(fn), list(cols) + [None], dropna=dropna, batch_size=64)
+    assert_frames_equal(positional(got), exp)
+    g = df.groupby("A", dropna=dropna)
+    pexp = pd.DataFrame({"key": g.B.sum().index.to_numpy(dtype="float64", na_value=np.nan), "f0": g.B.sum().to_numpy(dtype="float64"),
+                         "f1": g.B.mean().to_numpy(dtype="float64", na_value=np.nan), "f2": g.B.count().to_numpy()})
+    pgot = positional(got)[["key", "f0", "f1", "f2"]]
+    pgot["key"] = pgot["key"].to_numpy(dtype="float64", na_value=np.nan)
+    assert_frames_equal(pgot, pexp)
+
+
+def test_int64_sum_wraps_and_extreme_keys(gpu_lib, oracle):
+    # int64 SUM accumulates in int64 with wraparound (casted_aggfunc, -fwrapv); INT64_MIN is the table's
+    # free-slot marker, so it exercises the dedicated slot.
+    keys = np.array([np.iinfo(np.int64).min, np.iinfo(np.int64).max, 0, -1, np.iinfo(np.int64).min, 0] * 50, dtype=np.int64)
+    vals = np.array([2**62, 2**62, 2**62, -(2**62), 2**62, 2**62] * 50, dtype=np.int64)
+    t = Table.from_pandas(pd.DataFrame({"k": keys, "v": vals}))
+    got = stream_groupby(t, (0,), ("sum", "count"), (0, 1, 2), (1, 1), batch_size=100)
+    assert_frames_equal(positional(got), oracle_groupby_frame(oracle, t, 0, ["sum", "count"], [1, 1], batch_size=100))
+
+
+def test_empty_and_ragged_batches(gpu_lib):
+    df = pd.DataFrame({"A": np.array([5, 5, 7], dtype=np.int64), "B": np.array([1.0, 2.0, 4.0])})
+    t = Table.from_pandas(df)
+    from bodo_b200.streaming.groupby import (delete_groupby_state, groupby_build_consume_batch,
+                                             groupby_produce_output_batch, init_groupby_state)
+    st = init_groupby_state(-1, (0,), ("sum",), (0, 1), (1,))
+    groupby_build_consume_batch(st, t.slice(0, 0), False, True)   # empty batch first
+    groupby_build_consume_batch(st, t.slice(0, 2), False, True)
+    groupby_build_consume_batch(st, t.slice(2, 3), False, True)
+    last, _ = groupby_build_consume_batch(st, t.slice(3, 3), True, True)  # empty last batch
+    assert last
+    out, out_last = groupby_produce_output_batch(st, True)
+    assert out_last
+    assert_frames_equal(positional(out.to_pandas()), positional(df.groupby("A", as_index=False).B.sum()))
+    delete_groupby_state(st)
+    # a state that never saw a row produces an empty table
+    st = init_groupby_state(-1, (0,), ("sum",), (0, 1), (1,))
+    groupby_build_consume_batch(st, t.slice(0, 0), True, True)
+    out, out_last = groupby_produce_output_batch(st, True)
+    assert out_last and out.n_rows == 0
+    delete_groupby_state(st)
+
+
+@pytest.mark.parametrize("n_groups", [1, 30, 5000, 300000])
+def test_synthetic_vs_oracle_table_growth(gpu_lib, oracle, n_groups):
+    # seeded synthetic rows (same generator as bench.py); small expected_groups forces fail-list replays
+    # and table rebuilds (the reference's threshold-exceeded retry path, _groupby.cpp:3309-3341)
+    n = 1_000_000
+    k, v = oracle.synth_fill(0, n, n_groups, 7)
+    t = Table.from_pandas(pd.DataFrame({"k": k, "v": v}))
+    got = stream_groupby(t, (0,), ("sum", "count"), (0, 1, 2), (1, 1), batch_size=250_000, to_device=True, expected_groups=16,
+                         output_batch_size=4096)
+    exp = oracle_groupby_frame(oracle, t, 0, ["sum", "count"], [1, 1])
+    assert len(got) == min(n_groups, len(np.unique(k)))
+    assert_frames_equal(positional(got), exp)
+
+
+def test_float_sum_mean_tolerance(gpu_lib, oracle):
+    rng = np.random.default_rng(3)
+    n = 400_000
+    k = rng.integers(0, 1000, n).astype(np.int64)
+    v = rng.random(n)
+    v[rng.random(n) < 0.01] = np.nan
+    df = pd.DataFrame({"k": k, "v": v})
+    t = Table.from_pandas(df)
+    got = stream_groupby(t, (0,), ("sum", "mean", "min", "max", "count"), (0, 1, 2, 3, 4, 5), (1, 1, 1, 1, 1), batch_size=100_000)
+    exp = df.groupby("k", as_index=False).agg(f0=("v", "sum"), f1=("v", "mean"), f2=("v", "min"), f3=("v", "max"), f4=("v", "count"))
+    # float SUM/MEAN: atomics reorder the additions -> tolerance rtol 1e-5 / atol 1e-8 (bodo/tests/utils.py:179-180)
+    assert_frames_equal(positional(got), positional(exp), rtol=1e-5, atol=1e-8)
+
+
+def test_unsupported_function_fails_loudly(gpu_lib):
+    from bodo_b200 import B200Error
+    from bodo_b200.streaming.groupby import init_groupby_state
+    with pytest.raises(B200Error, match="unsupported aggregate function"):
+        init_groupby_state(-1, (0,), ("median",), (0, 1), (1,))
