@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — groupby-agg rows/sec on B200 (BASELINE.json metric), roofline and CPU baseline.
+
+Workload (config.workload): BASELINE.json configs[1] "2B-row int64 2-col, 1M-group groupby SUM/COUNT on
+1xB200"; with --gpus N > 1 it is configs[3] (the same 2B rows sharded across N GPUs, strong scaling, one
+hash-partition exchange of the partial aggregates over NCCL).  One step = one whole operator lifetime over
+the batch: init state -> consume all local rows -> (exchange) -> finalize -> produce.
+
+  value     rows/s with the input columns already resident in HBM (CUDA events, max over ranks)
+  e2e       rows/s through the same public API with HOST (pinned) input columns and a host copy of the result
+  roofline  consume kernel: 16 B/row (8 B key + 8 B value) / its mean launch time, measured with
+            CUDA events on the kernel's stream, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle (reference algorithm shape, one rank per host thread) on a bounded sample
+
+`--impl reference` times only that CPU restatement (the reference runtime cannot be built here: no MPI).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "groupby-agg rows/sec"
+UNIT = "rows/s"
+BYTES_PER_ROW = 16  # algorithmic bytes of the hash-aggregate scan
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=2_000_000_000, help="total rows over all GPUs")
+    ap.add_argument("--groups", type=int, default=1_000_000)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=256_000_000)
+    ap.add_argument("--ref-sample-rows", type=int, default=256_000_000)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.p = None
+        self.path = f"/tmp/b200_clocks_{os.getpid()}.csv"
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for ln in open(self.path):
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu_baseline(keys_np, vals_np, threads: int):
+    """Times the oracle's SPMD restatement; returns (rows/s, seconds, n_groups, checksums)."""
+    from oracle import oracle as O
+
+    t0 = time.perf_counter()
+    ng, cs = O.groupby_sum_count_mt(keys_np, vals_np, threads)
+    dt = time.perf_counter() - t0
+    return len(keys_np) / dt, dt, ng, cs
+
+
+def reference_arm(args):
+    """bench.py --impl reference: the reference's CPU algorithm (oracle port; the MPI runtime is unbuildable here,
+    DESIGN.md) on all host threads, each step one bounded sample of the same synthetic workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    threads = host_threads()
+    n = min(args.ref_sample_rows, args.rows)
+    keys, vals = O.synth_fill(0, n, args.groups, args.seed)
+    for _ in range(max(args.warmup, 0)):
+        run_cpu_baseline(keys, vals, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, ng, cs = run_cpu_baseline(keys, vals, threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"first {n} rows of the {args.rows}-row table per step, {args.groups} groups"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "rows": args.rows, "groups": args.groups, "aggs": ["sum", "count"],
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    if args.gpus == 1:
+        return f"{args.rows}-row int64 2-col, {args.groups}-group groupby SUM/COUNT on 1xB200 (BASELINE.json configs[1])"
+    return (f"{args.rows}-row {args.groups}-group groupby SUM/COUNT sharded across {args.gpus}xB200, hash-partition "
+            f"exchange of partial aggregates over NCCL (BASELINE.json configs[3])")
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from bodo_b200 import _lib, synth
+    from bodo_b200.streaming import groupby as G
+    from bodo_b200.table import Column, Table
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    _lib.require_gpu()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream(dev)
+    stream_ptr = stream.cuda_stream
+
+    # strong scaling: the 2B-row table is split into contiguous row slices (dist_get_start/end style)
+    chunk = (args.rows + world - 1) // world
+    row0 = min(rank * chunk, args.rows)
+    n_local = min(chunk, args.rows - row0)
+    keys = torch.empty(n_local, dtype=torch.int64, device=dev)
+    vals = torch.empty(n_local, dtype=torch.int64, device=dev)
+    synth.device_fill(keys, vals, row0, args.groups, args.seed, stream_ptr)
+    torch.cuda.synchronize(dev)
+    expect_sum = int(vals.sum().item())  # wraps like the int64 SUM does
+    table = Table([Column(keys), Column(vals)], ["key", "val"])
+    exp_groups_local = args.groups
+
+    stats = {}
+
+    def one_step(tab, collect=False, profile=False, to_host=False):
+        st = G.init_groupby_state(-1, (0,), ("sum", "count"), (0, 1, 2), (1, 1), parallel=world > 1, expected_groups=exp_groups_local,
+                                  output_batch_size=1 << 40, device=local_rank, stream=stream_ptr)
+        st._ensure(tab)
+        if profile:
+            G.get_metric(st, 100)
+        G.groupby_build_consume_batch(st, tab, True, True)
+        out, last = G.groupby_produce_output_batch(st, True)
+        assert last
+        res = None
+        if to_host:
+            res = [c.values_numpy(stream_ptr) for c in out.columns]
+            stats["d2h"] = sum(a.nbytes for a in res)
+        if collect:
+            cols = [torch.as_tensor(c.data, device=dev) for c in out.columns]
+            stats["n_out"] = out.n_rows
+            stats["sum_of_sums"] = int(cols[1].sum().item()) if out.n_rows else 0
+            stats["sum_of_counts"] = int(cols[2].sum().item()) if out.n_rows else 0
+            stats["launches"] = G.get_metric(st, 4)
+            if profile:
+                stats["consume_us"] = G.get_metric(st, 6)
+                stats["consume_launches"] = G.get_metric(st, 7)
+        G.delete_groupby_state(st)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 0)):
+        one_step(table)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        one_step(table)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+
+    # untimed: one profiled step (per-launch CUDA events inside the library) + result check
+    one_step(table, collect=True, profile=True)
+    barrier()
+    tot = torch.tensor([ms, float(stats["n_out"]), 0.0], dtype=torch.float64, device=dev)
+    chk = torch.tensor([stats["sum_of_sums"], stats["sum_of_counts"], expect_sum], dtype=torch.int64, device=dev)
+    if world > 1:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+        ms = float(mx[0].item())
+    n_groups_total = int(tot[1].item())
+    check_ok = int(chk[1].item()) == args.rows and int(chk[0].item()) == int(chk[2].item())
+
+    value = args.rows * args.steps / (ms * 1e-3)
+    peak, peak_kind = peaks()
+    kern_us = stats.get("consume_us", 0)
+    n_launch = max(stats.get("consume_launches", 1), 1)
+    achieved = (BYTES_PER_ROW * n_local / 1e9) / (kern_us * 1e-6) if kern_us else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "peak_kind": peak_kind, "kernel": "groupby_consume_i64_sumcount_kernel<true,true>",
+                "launches_per_step": n_launch, "avg_launch_ms": kern_us / 1e3 / n_launch,
+                "algorithmic_bytes_per_launch": BYTES_PER_ROW * n_local / n_launch}
+
+    # ---- e2e: same API, HOST (pinned) input columns, result copied back to the host every step ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            hk = torch.empty(n_local, dtype=torch.int64, pin_memory=True)
+            hv = torch.empty(n_local, dtype=torch.int64, pin_memory=True)
+            hk.copy_(keys); hv.copy_(vals)
+            torch.cuda.synchronize(dev)
+            htab = Table([Column(hk.numpy()), Column(hv.numpy())], ["key", "val"])
+            one_step(htab, to_host=True)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(args.e2e_steps):
+                one_step(htab, to_host=True)
+            e1.record(stream)
+            barrier()
+            wall = time.perf_counter() - t0
+            ems = max(e0.elapsed_time(e1), wall * 1e3 * 0.0)  # device span; host wall reported beside it
+            emax = torch.tensor([ems, wall * 1e3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+            ems, wall_ms = float(emax[0].item()), float(emax[1].item())
+            e2e = {"value": args.rows * args.e2e_steps / (max(ems, wall_ms) * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": 16 * n_local, "d2h_bytes_per_step": int(stats.get("d2h", 0)),
+                   "steps": args.e2e_steps, "ms_per_step": max(ems, wall_ms) / args.e2e_steps, "host_memory": "pinned"}
+            del hk, hv, htab
+        except Exception as ex:  # e.g. not enough pinnable host memory
+            e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+
+    # ---- CPU baseline on rank 0 at N == 1 ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ns = min(args.cpu_sample_rows, n_local)
+        kn = keys[:ns].cpu().numpy()
+        vn = vals[:ns].cpu().numpy()
+        threads = host_threads()
+        rps, secs, ng, cs = run_cpu_baseline(kn, vn, threads)
+        cpu = {"value": rps, "unit": UNIT, "cores": threads, "kind": "port", "seconds": secs,
+               "sample": f"first {ns} rows of the {args.rows}-row table, {ng} groups (oracle SPMD restatement, one rank per thread)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "rows": args.rows, "groups": args.groups, "aggs": ["sum", "count"],
+                       "rows_per_gpu": n_local, "l2": "inputs (16 B/row x rows_per_gpu) exceed the 126 MB L2; no flush needed",
+                       "step": "init state + consume + exchange + finalize + produce", "result_groups": n_groups_total,
+                       "result_check": "ok" if check_ok else "MISMATCH"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(stats.get("launches", 0)) * args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    if not check_ok:
+        sys.exit(3)
+
+
+if __name__ == "__main__":
+    main()

@@ -497,6 +497,18 @@ class GroupbyState {
     // metrics
     int64_t rows_consumed = 0, rebuilds = 0, launches = 0, fail_rows = 0;
     bool build_done = false;
+    // optional per-launch timing of the consume kernel (bench.py roofline): CUDA events on `stream`
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    int64_t consume_launches = 0;
+    double consume_kernel_us() {
+        double us = 0;
+        for (auto& pr : prof_events) {
+            float ms = 0;
+            if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) us += ms * 1000.0;
+        }
+        return us;
+    }
 
     GroupbyState(const int8_t* ct, const int8_t* at, int n_arrs, const int32_t* ftypes, const int32_t* f_in_offsets,
                  const int32_t* f_in_cols, int n_funcs_, uint64_t n_keys, int64_t out_bs, bool parallel_, bool dropna_,
@@ -572,6 +584,7 @@ class GroupbyState {
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         for (int b = 0; b < 2; b++) { if (stage_free[b]) cudaEventDestroy(stage_free[b]); if (stage_ready[b]) cudaEventDestroy(stage_ready[b]); }
         if (h_counters) cudaFreeHost(h_counters);
+        for (auto& pr : prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     }
 
     int grid_for(int64_t n, int per_thread = 1, int block = 256) const {
@@ -670,6 +683,11 @@ class GroupbyState {
         auto launch = [&](const uint32_t* index_list, int64_t rows) {
             long long* ctr = d_counters.as<long long>();
             long long limit = (long long)(cap / 2);
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (profiling && index_list == nullptr) {
+                B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1));
+                B200_CUDA(cudaEventRecord(ev0, stream));
+            }
             if (fast && index_list == nullptr) {
                 int g = grid_for(rows, 2);
                 const long long* k = (const long long*)data[0];
@@ -697,6 +715,8 @@ class GroupbyState {
                 groupby_consume_kernel<<<grid_for(rows), 256, 0, stream>>>(a);
             }
             launches++;
+            if (index_list == nullptr) consume_launches++;
+            if (ev0) { B200_CUDA(cudaEventRecord(ev1, stream)); prof_events.emplace_back(ev0, ev1); }
             B200_CUDA(cudaGetLastError());
         };
         launch(nullptr, n);
@@ -1002,6 +1022,9 @@ int64_t b200_groupby_get_metric(void* state, int32_t which) {
         case 3: return s->rebuilds;
         case 4: return s->launches;
         case 5: return s->fail_rows;
+        case 6: return (int64_t)s->consume_kernel_us();
+        case 7: return s->consume_launches;
+        case 100: s->profiling = true; return 0;
         default: return -1;
     }
 }

@@ -105,7 +105,9 @@ int b200_groupby_produce_output_batch(void* state, b200_table* out, int32_t* out
 void b200_delete_groupby_state(void* state);
 
 /* Metrics (subset of GroupbyMetrics, streaming/_groupby.h:106-223): 0 n_groups, 1 table capacity,
- * 2 rows consumed, 3 table rebuilds, 4 kernel launches so far, 5 rows taken by the fallback list. */
+ * 2 rows consumed, 3 table rebuilds, 4 kernel launches so far, 5 rows replayed from the fail list,
+ * 6 accumulated device time of the consume kernel in microseconds (CUDA events on the state's stream;
+ * only when profiling was enabled by querying metric 100 first), 7 consume-kernel launches. */
 int64_t b200_groupby_get_metric(void* state, int32_t which);
 
 /* ---- streaming hash join (reference: bodo/libs/streaming/_join.cpp) ---- */
