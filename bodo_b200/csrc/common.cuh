@@ -41,7 +41,7 @@ struct Error : std::runtime_error {
         if (!(cond)) throw b200::Error(std::string(msg)); \
     } while (0)
 
-inline int ctype_size(int ct) {
+__host__ __device__ inline int ctype_size(int ct) {
     switch (ct) {
         case CT_INT8: case CT_UINT8: case CT_BOOL: return 1;
         case CT_INT16: case CT_UINT16: return 2;
@@ -50,7 +50,7 @@ inline int ctype_size(int ct) {
         default: return 0;
     }
 }
-inline bool ctype_is_float(int ct) { return ct == CT_FLOAT32 || ct == CT_FLOAT64; }
+__host__ __device__ inline bool ctype_is_float(int ct) { return ct == CT_FLOAT32 || ct == CT_FLOAT64; }
 inline bool ctype_is_signed_int(int ct) {
     return ct == CT_INT8 || ct == CT_INT16 || ct == CT_INT32 || ct == CT_INT64 || ct == CT_DATE || ct == CT_DATETIME ||
            ct == CT_TIMEDELTA;

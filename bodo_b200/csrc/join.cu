@@ -1,9 +1,641 @@
-// join.cu — streaming hash join (placeholder until the kernels land; fails loudly).
+// join.cu — streaming hash join on one B200 (sm_100a).
+//
+// Replaces HashJoinState / JoinPartition of the reference (bodo/libs/streaming/_join.cpp):
+//   build  : join_build_consume_batch (:3134-3443) appends batches to device-resident build columns; on the
+//            last batch BuildHashTable (:381-437) + FinalizeGroups (:439-512) become three kernels:
+//            insert+count (one table slot per distinct key, rows-per-key counter), exclusive scan (CSR
+//            groups_offsets), fill (CSR groups = build row ids).  Keys with exactly one build row keep the
+//            row id in the slot itself, so the common 1:N probe needs no CSR lookup.
+//   probe  : join_probe_consume_batch (:3459-3900): pass A looks up every probe row and writes its match count,
+//            a scan turns counts into output offsets, pass B expands the matches and gathers the kept build and
+//            probe columns straight into the output columns (produce_probe_output :729-827 +
+//            ChunkedTableBuilder::AppendJoinOutput fused; no (build_idx, probe_idx) pair vectors in HBM,
+//            unlike the cuDF path bodo/libs/streaming/cuda_join.cpp:543-612).
+//   outer  : probe_table_outer emits unmatched probe rows with NULL build columns; build_table_outer tracks
+//            matched build rows and emits the unmatched ones after the last probe batch.
+// NA keys match NA keys (pandas semantics, is_na_equal = true, bodo/pandas/physical/join.h:267).
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
-extern "C" {
-void* b200_join_state_init(int64_t, const int8_t*, const int8_t*, int32_t, const int8_t*, const int8_t*, int32_t, uint64_t, int32_t, int32_t, int64_t, int32_t, int64_t, void*) { b200::set_last_error("b200 join: not implemented yet"); return nullptr; }
-int b200_join_build_consume_batch(void*, const b200_table*, int32_t, int32_t*) { b200::set_last_error("b200 join: not implemented yet"); return -1; }
-int b200_join_probe_consume_batch(void*, const b200_table*, const uint64_t*, int64_t, const uint64_t*, int64_t, b200_table*, int64_t*, int32_t, int32_t*) { b200::set_last_error("b200 join: not implemented yet"); return -1; }
-void b200_delete_join_state(void*) {}
-int64_t b200_join_get_metric(void*, int32_t) { return -1; }
+
+namespace b200 {
+
+constexpr long long J_EMPTY = (long long)0x8000000000000000ULL;
+constexpr int J_MAX_COLS = 32;
+constexpr uint32_t J_NONE = 0xffffffffu;
+
+// ---- exclusive scan u32 -> u64 (reduce / scan-of-sums / scan), tile = 2048 elements per CTA ----
+constexpr int SCAN_TILE = 2048;
+__global__ void __launch_bounds__(256) scan_reduce_kernel(const uint32_t* in, int64_t n, unsigned long long* block_sums) {
+    __shared__ unsigned long long sh[256];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    unsigned long long s = 0;
+    for (int k = threadIdx.x; k < SCAN_TILE; k += 256) { int64_t i = base + k; if (i < n) s += in[i]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = sh[0];
 }
+__global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned long long* block_sums, int64_t nb, unsigned long long* total) {
+    // single CTA: each thread owns a contiguous run of block sums
+    __shared__ unsigned long long sh[1024];
+    int64_t per = (nb + 1023) / 1024;
+    int64_t b0 = threadIdx.x * per, b1 = b0 + per < nb ? b0 + per : nb;
+    unsigned long long s = 0;
+    for (int64_t b = b0; b < b1; b++) s += block_sums[b];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    // inclusive Hillis-Steele over 1024 partials
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned long long v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned long long run = threadIdx.x ? sh[threadIdx.x - 1] : 0;
+    for (int64_t b = b0; b < b1; b++) { unsigned long long v = block_sums[b]; block_sums[b] = run; run += v; }
+    if (threadIdx.x == 1023) *total = sh[1023];
+}
+__global__ void __launch_bounds__(256) scan_apply_kernel(const uint32_t* in, int64_t n, const unsigned long long* block_sums,
+                                                         unsigned long long* out) {
+    __shared__ unsigned long long sh[256];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    constexpr int PER = SCAN_TILE / 256;
+    uint32_t v[PER];
+    unsigned long long s = 0;
+    int64_t i0 = base + (int64_t)threadIdx.x * PER;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        unsigned long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    unsigned long long run = block_sums[blockIdx.x] + (threadIdx.x ? sh[threadIdx.x - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < PER; k++) { if (i0 + k < n) out[i0 + k] = run; run += v[k]; }
+}
+
+struct Scanner {
+    DevBuf sums, total;
+    unsigned long long* h_total = nullptr;
+    ~Scanner() { if (h_total) cudaFreeHost(h_total); }
+    // out[i] = sum_{j<i} in[j]; returns the grand total (synchronises the stream)
+    unsigned long long run(const uint32_t* in, int64_t n, unsigned long long* out, cudaStream_t st, int64_t* launches) {
+        if (!h_total) B200_CUDA(cudaMallocHost((void**)&h_total, 8));
+        if (n == 0) return 0;
+        int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+        sums.ensure((size_t)nb * 8);
+        total.ensure(8);
+        scan_reduce_kernel<<<(unsigned)nb, 256, 0, st>>>(in, n, sums.as<unsigned long long>());
+        scan_sums_kernel<<<1, 1024, 0, st>>>(sums.as<unsigned long long>(), nb, total.as<unsigned long long>());
+        scan_apply_kernel<<<(unsigned)nb, 256, 0, st>>>(in, n, sums.as<unsigned long long>(), out);
+        *launches += 3;
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaMemcpyAsync(h_total, total.p, 8, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        return *h_total;
+    }
+};
+
+// ---- hash table ----
+struct SlotInfo { uint32_t cnt; uint32_t first; };  // rows with this key; one of those rows (row id)
+
+__device__ __forceinline__ uint64_t j_hash_slot(long long key, uint64_t mask) {
+    return (xxh3_64_short((uint64_t)key, 8, SEED_HASH_JOIN) >> 32) & mask;
+}
+// capacity >= 2 * n_build, so an insert always finds a free slot
+__device__ __forceinline__ uint32_t j_find_or_insert(long long* tkeys, uint64_t cap, long long key) {
+    uint64_t mask = cap - 1, s = j_hash_slot(key, mask);
+    while (true) {
+        long long k = __ldcg(tkeys + s);
+        if (k == key) return (uint32_t)s;
+        if (k == J_EMPTY) {
+            long long prev = (long long)atomicCAS((unsigned long long*)(tkeys + s), (unsigned long long)J_EMPTY, (unsigned long long)key);
+            if (prev == J_EMPTY || prev == key) return (uint32_t)s;
+        }
+        s = (s + 1) & mask;
+    }
+}
+__device__ __forceinline__ uint32_t j_find(const long long* __restrict__ tkeys, uint64_t cap, long long key) {
+    uint64_t mask = cap - 1, s = j_hash_slot(key, mask);
+    while (true) {
+        long long k = __ldg(tkeys + s);
+        if (k == key) return (uint32_t)s;
+        if (k == J_EMPTY) return J_NONE;
+        s = (s + 1) & mask;
+    }
+}
+
+// BuildHashTable: slot per distinct key, num_rows_in_group, build_row_to_group_map (= row_slot)
+__global__ void join_insert_count_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid_bytes, int64_t n,
+                                         long long* tkeys, uint64_t cap, SlotInfo* info, uint32_t* row_slot) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t s;
+        if (key_valid_bytes && !key_valid_bytes[i]) s = (uint32_t)cap;  // NA group
+        else {
+            long long key = load_int_as_i64(key_data, key_ctype, i);
+            s = key == J_EMPTY ? (uint32_t)cap + 1 : j_find_or_insert(tkeys, cap, key);
+        }
+        row_slot[i] = s;
+        atomicAdd(&info[s].cnt, 1u);
+        info[s].first = (uint32_t)i;  // any row of the group; exact when cnt == 1
+    }
+}
+__global__ void join_slot_counts_kernel(const SlotInfo* info, uint64_t n_slots, uint32_t* cnt_multi) {
+    // CSR only holds groups with more than one row
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += stride) {
+        uint32_t c = info[s].cnt;
+        cnt_multi[s] = c > 1 ? c : 0;
+    }
+}
+// FinalizeGroups: groups[offs[slot] + k] = k-th build row of the slot's key
+__global__ void join_fill_groups_kernel(const uint32_t* row_slot, int64_t n, const SlotInfo* info, const unsigned long long* offs,
+                                        uint32_t* fill, uint32_t* groups) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t s = row_slot[i];
+        if (info[s].cnt > 1) groups[offs[s] + atomicAdd(&fill[s], 1u)] = (uint32_t)i;
+    }
+}
+
+// probe pass A: slot + match count per probe row
+__global__ void join_probe_count_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid, int64_t n,
+                                        const long long* tkeys, uint64_t cap, const SlotInfo* info, int probe_outer,
+                                        uint32_t* pslot, uint32_t* pcnt) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t s;
+        if (!bit_valid(key_valid, i)) s = (uint32_t)cap;
+        else {
+            long long key = load_int_as_i64(key_data, key_ctype, i);
+            s = key == J_EMPTY ? (uint32_t)cap + 1 : j_find(tkeys, cap, key);
+        }
+        uint32_t c = s == J_NONE ? 0 : info[s].cnt;
+        if (c == 0) s = J_NONE;
+        pslot[i] = s;
+        pcnt[i] = c ? c : (probe_outer ? 1u : 0u);
+    }
+}
+
+struct GatherArgs {
+    int64_t n_probe;
+    const uint32_t* pslot;
+    const unsigned long long* poff;
+    const SlotInfo* info;
+    const unsigned long long* goffs;
+    const uint32_t* groups;
+    uint8_t* bmatched;  // build_outer: matched flags per build row, else nullptr
+    int n_b, n_p;       // kept build / probe columns
+    const void* b_data[J_MAX_COLS]; const uint8_t* b_valid[J_MAX_COLS]; int b_size[J_MAX_COLS];
+    const void* p_data[J_MAX_COLS]; const uint8_t* p_valid[J_MAX_COLS]; int p_size[J_MAX_COLS];
+    void* ob_data[J_MAX_COLS]; uint8_t* ob_valid[J_MAX_COLS];  // output columns (validity: one byte per row or nullptr)
+    void* op_data[J_MAX_COLS]; uint8_t* op_valid[J_MAX_COLS];
+};
+__device__ __forceinline__ void copy_item(void* dst, int64_t d, const void* src, int64_t s, int size) {
+    switch (size) {
+        case 8: ((uint64_t*)dst)[d] = ((const uint64_t*)src)[s]; break;
+        case 4: ((uint32_t*)dst)[d] = ((const uint32_t*)src)[s]; break;
+        case 2: ((uint16_t*)dst)[d] = ((const uint16_t*)src)[s]; break;
+        default: ((uint8_t*)dst)[d] = ((const uint8_t*)src)[s]; break;
+    }
+}
+__device__ __forceinline__ void zero_item(void* dst, int64_t d, int size) {
+    switch (size) {
+        case 8: ((uint64_t*)dst)[d] = 0; break;
+        case 4: ((uint32_t*)dst)[d] = 0; break;
+        case 2: ((uint16_t*)dst)[d] = 0; break;
+        default: ((uint8_t*)dst)[d] = 0; break;
+    }
+}
+// probe pass B: expand matches and gather both sides into the output columns (build validity is byte-per-row)
+__global__ void __launch_bounds__(256) join_probe_gather_kernel(const __grid_constant__ GatherArgs a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_probe; i += stride) {
+        uint32_t s = a.pslot[i];
+        unsigned long long o = a.poff[i];
+        uint32_t c = s == J_NONE ? 0 : a.info[s].cnt;
+        uint32_t reps = c ? c : (a.poff[i + 1] - o ? 1u : 0u);  // outer probe row without match: one NULL-build row
+        for (uint32_t q = 0; q < reps; q++) {
+            int64_t orow = (int64_t)(o + q);
+            if (c) {
+                uint32_t brow = c == 1 ? a.info[s].first : a.groups[a.goffs[s] + q];
+                if (a.bmatched) a.bmatched[brow] = 1;
+                for (int k = 0; k < a.n_b; k++) {
+                    copy_item(a.ob_data[k], orow, a.b_data[k], brow, a.b_size[k]);
+                    if (a.ob_valid[k]) a.ob_valid[k][orow] = a.b_valid[k] ? a.b_valid[k][brow] : 1;
+                }
+            } else {
+                for (int k = 0; k < a.n_b; k++) { zero_item(a.ob_data[k], orow, a.b_size[k]); a.ob_valid[k][orow] = 0; }
+            }
+            for (int k = 0; k < a.n_p; k++) {
+                copy_item(a.op_data[k], orow, a.p_data[k], i, a.p_size[k]);
+                if (a.op_valid[k]) a.op_valid[k][orow] = bit_valid(a.p_valid[k], i) ? 1 : 0;
+            }
+        }
+    }
+}
+
+// build_outer tail: unmatched build rows with NULL probe columns
+__global__ void join_unmatched_flags_kernel(const uint8_t* bmatched, int64_t n, uint32_t* flags) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) flags[i] = bmatched[i] ? 0u : 1u;
+}
+struct TailArgs {
+    int64_t n_build;
+    const uint32_t* flags;
+    const unsigned long long* off;
+    int n_b, n_p;
+    const void* b_data[J_MAX_COLS]; const uint8_t* b_valid[J_MAX_COLS]; int b_size[J_MAX_COLS];
+    int p_size[J_MAX_COLS];
+    void* ob_data[J_MAX_COLS]; uint8_t* ob_valid[J_MAX_COLS];
+    void* op_data[J_MAX_COLS]; uint8_t* op_valid[J_MAX_COLS];
+};
+__global__ void join_unmatched_emit_kernel(const __grid_constant__ TailArgs a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_build; i += stride) {
+        if (!a.flags[i]) continue;
+        int64_t orow = (int64_t)a.off[i];
+        for (int k = 0; k < a.n_b; k++) {
+            copy_item(a.ob_data[k], orow, a.b_data[k], i, a.b_size[k]);
+            if (a.ob_valid[k]) a.ob_valid[k][orow] = a.b_valid[k] ? a.b_valid[k][i] : 1;
+        }
+        for (int k = 0; k < a.n_p; k++) { zero_item(a.op_data[k], orow, a.p_size[k]); a.op_valid[k][orow] = 0; }
+    }
+}
+
+__global__ void expand_bitmap_kernel(const uint8_t* bitmap, int64_t n, uint8_t* bytes) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) bytes[i] = bit_valid(bitmap, i) ? 1 : 0;
+}
+__global__ void pack_bitmap_kernel(const uint8_t* bytes, int64_t n, uint32_t* words) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t n_round = (n + 31) & ~31ll;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        unsigned m = __ballot_sync(0xffffffffu, i < n && bytes[i]);
+        if ((threadIdx.x & 31) == 0) words[i >> 5] = m;
+    }
+}
+__global__ void fill_i64_kernel(long long* p, uint64_t n, long long v) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+// ================================================================================================
+struct GrowCol {  // growable device column (geometric growth, copy on grow)
+    DevBuf buf;
+    size_t used = 0;
+    void append(const void* src, size_t nbytes, bool src_is_host, cudaStream_t st) {
+        if (used + nbytes > buf.bytes) {
+            DevBuf nb;
+            nb.alloc(std::max<size_t>((used + nbytes) * 2, 1 << 16));
+            if (used) B200_CUDA(cudaMemcpyAsync(nb.p, buf.p, used, cudaMemcpyDeviceToDevice, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            buf = std::move(nb);
+        }
+        if (nbytes) B200_CUDA(cudaMemcpyAsync((char*)buf.p + used, src, nbytes, src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+        used += nbytes;
+    }
+    void reserve(size_t n) { if (n > buf.bytes) { B200_REQUIRE(used == 0, "internal: reserve after append"); buf.alloc(n); } }
+};
+
+class JoinState {
+   public:
+    int device; cudaStream_t stream; int sms;
+    std::vector<int8_t> b_ct, b_at, p_ct, p_at;
+    int n_b, n_p;
+    bool build_outer, probe_outer;
+    int64_t output_batch_size;
+    // build side
+    std::vector<GrowCol> bcol, bvalid;  // data; validity as one byte per row (empty when the column has none so far)
+    std::vector<bool> b_has_valid;
+    int64_t n_build = 0;
+    bool build_final = false;
+    uint64_t cap = 0;
+    DevBuf d_tkeys, d_info, d_row_slot, d_cnt_multi, d_goffs, d_groups, d_fill, d_bmatched;
+    Scanner scan;
+    // probe scratch + output
+    DevBuf d_pslot, d_pcnt, d_poff, d_stage_valid;
+    std::vector<DevBuf> stage_data, stage_valid;   // device copies of host probe batches
+    std::vector<DevBuf> out_data, out_vbytes, out_bitmap;
+    int64_t launches = 0, probe_rows = 0, out_rows_total = 0;
+    bool tail_emitted = false;
+
+    JoinState(const int8_t* bct, const int8_t* bat, int nb, const int8_t* pct, const int8_t* pat, int np, uint64_t n_keys,
+              bool bo, bool po, int64_t obs, int dev, int64_t expected_build_rows, cudaStream_t st)
+        : device(dev), stream(st), n_b(nb), n_p(np), build_outer(bo), probe_outer(po), output_batch_size(obs) {
+        B200_REQUIRE(n_keys == 1, "b200 join: exactly one key column is supported (multi-key is a 'next' row, SURVEY.md §8f)");
+        B200_REQUIRE(nb >= 1 && np >= 1 && nb <= J_MAX_COLS && np <= J_MAX_COLS, "b200 join: between 1 and 32 columns per side");
+        b_ct.assign(bct, bct + nb); b_at.assign(bat, bat + nb); p_ct.assign(pct, pct + np); p_at.assign(pat, pat + np);
+        for (int c = 0; c < nb; c++) B200_REQUIRE(ctype_size(b_ct[c]) > 0, "b200 join: unsupported build column dtype");
+        for (int c = 0; c < np; c++) B200_REQUIRE(ctype_size(p_ct[c]) > 0, "b200 join: unsupported probe column dtype");
+        B200_REQUIRE(!ctype_is_float(b_ct[0]) && !ctype_is_float(p_ct[0]), "b200 join: key columns must be integer/date typed");
+        B200_REQUIRE(ctype_size(b_ct[0]) == ctype_size(p_ct[0]), "b200 join: build and probe key widths differ");
+        B200_CUDA(cudaSetDevice(device));
+        sms = num_sms(device);
+        bcol.resize(nb); bvalid.resize(nb); b_has_valid.assign(nb, false);
+        if (expected_build_rows > 0)
+            for (int c = 0; c < nb; c++) bcol[c].reserve((size_t)expected_build_rows * ctype_size(b_ct[c]));
+        out_data.resize(nb + np); out_vbytes.resize(nb + np); out_bitmap.resize(nb + np);
+        stage_data.resize(std::max(nb, np)); stage_valid.resize(std::max(nb, np));
+    }
+    ~JoinState() { cudaSetDevice(device); cudaStreamSynchronize(stream); }
+
+    int grid_for(int64_t n) const { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sms * 8)); }
+
+    // device pointers for a batch (host batches are staged to the device first)
+    void stage_batch(const b200_table* t, int ncols, const std::vector<int8_t>& cts, std::vector<const void*>& data,
+                     std::vector<const uint8_t*>& valid) {
+        data.assign(ncols, nullptr); valid.assign(ncols, nullptr);
+        int64_t n = t->n_rows;
+        for (int c = 0; c < ncols; c++) {
+            B200_REQUIRE(t->cols[c].c_type == cts[c], "b200 join: batch column dtype differs from the schema");
+            if (t->device >= 0) {
+                B200_REQUIRE(t->device == device, "b200 join: batch lives on another device");
+                data[c] = t->cols[c].data; valid[c] = t->cols[c].validity;
+            } else {
+                size_t nbytes = (size_t)n * ctype_size(cts[c]);
+                stage_data[c].ensure(nbytes + 8);
+                if (nbytes) B200_CUDA(cudaMemcpyAsync(stage_data[c].p, t->cols[c].data, nbytes, cudaMemcpyHostToDevice, stream));
+                data[c] = stage_data[c].p;
+                if (t->cols[c].validity) {
+                    stage_valid[c].ensure((size_t)(n + 7) / 8 + 8);
+                    B200_CUDA(cudaMemcpyAsync(stage_valid[c].p, t->cols[c].validity, (size_t)(n + 7) / 8, cudaMemcpyHostToDevice, stream));
+                    valid[c] = stage_valid[c].as<uint8_t>();
+                }
+            }
+        }
+    }
+
+    void build_consume(const b200_table* t, bool is_last) {
+        B200_REQUIRE(!build_final, "b200 join: build batch after the build was finalized");
+        B200_REQUIRE(t->n_cols == n_b, "b200 join: build batch has a different number of columns than the schema");
+        B200_CUDA(cudaSetDevice(device));
+        int64_t n = t->n_rows;
+        B200_REQUIRE(n_build + n < (1ll << 32) - 2, "b200 join: build side is limited to 2^32 - 2 rows per GPU");
+        if (n > 0) {
+            std::vector<const void*> data; std::vector<const uint8_t*> valid;
+            stage_batch(t, n_b, b_ct, data, valid);
+            for (int c = 0; c < n_b; c++) {
+                bcol[c].append(data[c], (size_t)n * ctype_size(b_ct[c]), false, stream);
+                bool has = valid[c] != nullptr;
+                if (has && !b_has_valid[c]) {  // first batch with a bitmap: earlier rows were all valid
+                    b_has_valid[c] = true;
+                    if (n_build) { DevBuf ones; ones.alloc((size_t)n_build); B200_CUDA(cudaMemsetAsync(ones.p, 1, (size_t)n_build, stream)); bvalid[c].append(ones.p, (size_t)n_build, false, stream); B200_CUDA(cudaStreamSynchronize(stream)); }
+                }
+                if (b_has_valid[c]) {
+                    d_stage_valid.ensure((size_t)n);
+                    if (has) { expand_bitmap_kernel<<<grid_for(n), 256, 0, stream>>>(valid[c], n, d_stage_valid.as<uint8_t>()); launches++; }
+                    else B200_CUDA(cudaMemsetAsync(d_stage_valid.p, 1, (size_t)n, stream));
+                    bvalid[c].append(d_stage_valid.p, (size_t)n, false, stream);
+                }
+            }
+            B200_CUDA(cudaStreamSynchronize(stream));  // staging buffers are reused by the next batch
+            n_build += n;
+        }
+        if (is_last) finalize_build();
+    }
+
+    void finalize_build() {
+        cap = 1024;
+        while (cap < 2ull * (uint64_t)n_build) cap <<= 1;
+        uint64_t n_slots = cap + 2;
+        d_tkeys.alloc(n_slots * 8);
+        fill_i64_kernel<<<grid_for((int64_t)n_slots), 256, 0, stream>>>(d_tkeys.as<long long>(), n_slots, J_EMPTY);
+        d_info.alloc(n_slots * sizeof(SlotInfo));
+        B200_CUDA(cudaMemsetAsync(d_info.p, 0, n_slots * sizeof(SlotInfo), stream));
+        d_row_slot.alloc((size_t)std::max<int64_t>(n_build, 1) * 4);
+        launches++;
+        if (n_build > 0) {
+            join_insert_count_kernel<<<grid_for(n_build), 256, 0, stream>>>(bcol[0].buf.p, b_ct[0], b_has_valid[0] ? bvalid[0].buf.as<uint8_t>() : nullptr,
+                                                                           n_build, d_tkeys.as<long long>(), cap, d_info.as<SlotInfo>(), d_row_slot.as<uint32_t>());
+            d_cnt_multi.alloc(n_slots * 4);
+            join_slot_counts_kernel<<<grid_for((int64_t)n_slots), 256, 0, stream>>>(d_info.as<SlotInfo>(), n_slots, d_cnt_multi.as<uint32_t>());
+            launches += 2;
+            d_goffs.alloc((n_slots + 1) * 8);
+            unsigned long long n_multi = scan.run(d_cnt_multi.as<uint32_t>(), (int64_t)n_slots, d_goffs.as<unsigned long long>(), stream, &launches);
+            d_groups.alloc((size_t)std::max<unsigned long long>(n_multi, 1) * 4);
+            if (n_multi > 0) {
+                d_fill.alloc(n_slots * 4);
+                B200_CUDA(cudaMemsetAsync(d_fill.p, 0, n_slots * 4, stream));
+                join_fill_groups_kernel<<<grid_for(n_build), 256, 0, stream>>>(d_row_slot.as<uint32_t>(), n_build, d_info.as<SlotInfo>(), d_goffs.as<unsigned long long>(),
+                                                                              d_fill.as<uint32_t>(), d_groups.as<uint32_t>());
+                launches++;
+            }
+            d_cnt_multi.release(); d_fill.release(); d_row_slot.release();
+        } else {
+            d_goffs.alloc(8); d_groups.alloc(8);
+        }
+        if (build_outer) { d_bmatched.alloc((size_t)std::max<int64_t>(n_build, 1)); B200_CUDA(cudaMemsetAsync(d_bmatched.p, 0, (size_t)std::max<int64_t>(n_build, 1), stream)); }
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaStreamSynchronize(stream));
+        build_final = true;
+    }
+
+    // describes output column k (0..n_kb-1 build, then probe) in `out`
+    void describe_out(b200_table* out, const std::vector<int>& kb, const std::vector<int>& kp, int64_t rows) {
+        out->n_rows = rows; out->n_cols = (int)(kb.size() + kp.size()); out->device = device;
+        for (size_t k = 0; k < kb.size() + kp.size(); k++) {
+            bool is_b = k < kb.size();
+            int src = is_b ? kb[k] : kp[k - kb.size()];
+            b200_column& c = out->cols[k];
+            c.data = out_data[k].p; c.length = rows;
+            c.c_type = is_b ? b_ct[src] : p_ct[src];
+            bool nullable = out_vbytes[k].p != nullptr && out_has_valid[k];
+            c.validity = nullable ? out_bitmap[k].as<uint8_t>() : nullptr;
+            c.arr_type = nullable ? ARR_NULLABLE : (is_b ? b_at[src] : p_at[src]);
+        }
+    }
+    std::vector<bool> out_has_valid;
+
+    int64_t probe_consume(const b200_table* t, const uint64_t* kept_b, int64_t n_kb, const uint64_t* kept_p, int64_t n_kp,
+                          b200_table* out, bool is_last) {
+        B200_REQUIRE(build_final, "b200 join: probe before the build side was finished (is_last build batch)");
+        B200_REQUIRE(t->n_cols == n_p, "b200 join: probe batch has a different number of columns than the schema");
+        B200_REQUIRE(out->cols != nullptr, "b200 join: out->cols must point to n_kept_build + n_kept_probe descriptors");
+        B200_CUDA(cudaSetDevice(device));
+        std::vector<int> kb, kp;
+        for (int64_t k = 0; k < n_kb; k++) { B200_REQUIRE((int)kept_b[k] < n_b, "b200 join: bad kept build column"); kb.push_back((int)kept_b[k]); }
+        for (int64_t k = 0; k < n_kp; k++) { B200_REQUIRE((int)kept_p[k] < n_p, "b200 join: bad kept probe column"); kp.push_back((int)kept_p[k]); }
+        int n_out_cols = (int)(kb.size() + kp.size());
+        B200_REQUIRE(n_out_cols <= J_MAX_COLS, "b200 join: too many output columns");
+        int64_t n = t->n_rows;
+        std::vector<const void*> data; std::vector<const uint8_t*> valid;
+        stage_batch(t, n_p, p_ct, data, valid);
+        // pass A + scan
+        unsigned long long n_match = 0;
+        d_pslot.ensure((size_t)(n + 1) * 4); d_pcnt.ensure((size_t)(n + 1) * 4); d_poff.ensure((size_t)(n + 2) * 8);
+        if (n > 0) {
+            join_probe_count_kernel<<<grid_for(n), 256, 0, stream>>>(data[0], p_ct[0], valid[0], n, d_tkeys.as<long long>(), cap, d_info.as<SlotInfo>(),
+                                                                     probe_outer ? 1 : 0, d_pslot.as<uint32_t>(), d_pcnt.as<uint32_t>());
+            launches++;
+            B200_CUDA(cudaMemsetAsync(d_pcnt.as<uint32_t>() + n, 0, 4, stream));
+            n_match = scan.run(d_pcnt.as<uint32_t>(), n + 1, d_poff.as<unsigned long long>(), stream, &launches);
+        }
+        // unmatched build rows go out with the last probe batch
+        unsigned long long n_tail = 0;
+        DevBuf tail_flags, tail_off;
+        if (is_last && build_outer && !tail_emitted && n_build > 0) {
+            tail_flags.alloc((size_t)(n_build + 1) * 4); tail_off.alloc((size_t)(n_build + 2) * 8);
+        }
+        // which output columns carry validity: nullable inputs, NULL-extended sides of an outer join
+        out_has_valid.assign(n_out_cols, false);
+        for (int k = 0; k < n_out_cols; k++) {
+            bool is_b = k < (int)kb.size();
+            int src = is_b ? kb[k] : kp[k - kb.size()];
+            out_has_valid[k] = is_b ? (b_has_valid[src] || b_at[src] == ARR_NULLABLE || probe_outer)
+                                    : (valid[src] != nullptr || p_at[src] == ARR_NULLABLE || build_outer);
+        }
+        auto ensure_out = [&](int64_t rows) {
+            for (int k = 0; k < n_out_cols; k++) {
+                bool is_b = k < (int)kb.size();
+                int src = is_b ? kb[k] : kp[k - kb.size()];
+                out_data[k].ensure((size_t)(rows + 32) * ctype_size(is_b ? b_ct[src] : p_ct[src]));
+                if (out_has_valid[k]) { out_vbytes[k].ensure((size_t)rows + 32); out_bitmap[k].ensure((size_t)((rows + 31) / 32 + 1) * 4); }
+            }
+        };
+        // pass B needs bmatched complete before the tail is computed, so: gather first, then the tail
+        GatherArgs g{};
+        g.n_probe = n; g.pslot = d_pslot.as<uint32_t>(); g.poff = d_poff.as<unsigned long long>(); g.info = d_info.as<SlotInfo>();
+        g.goffs = d_goffs.as<unsigned long long>(); g.groups = d_groups.as<uint32_t>(); g.bmatched = build_outer ? d_bmatched.as<uint8_t>() : nullptr;
+        g.n_b = (int)kb.size(); g.n_p = (int)kp.size();
+        // the tail size is only known after the gather; grow the output (keeping the gathered rows) if needed
+        ensure_out((int64_t)n_match);
+        for (int k = 0; k < n_out_cols; k++) {
+            bool is_b = k < (int)kb.size();
+            int src = is_b ? kb[k] : kp[k - kb.size()];
+            if (is_b) {
+                int j = k;
+                g.b_data[j] = bcol[src].buf.p; g.b_valid[j] = b_has_valid[src] ? bvalid[src].buf.as<uint8_t>() : nullptr; g.b_size[j] = ctype_size(b_ct[src]);
+                g.ob_data[j] = out_data[k].p; g.ob_valid[j] = out_has_valid[k] ? out_vbytes[k].as<uint8_t>() : nullptr;
+            } else {
+                int j = k - (int)kb.size();
+                g.p_data[j] = data[src]; g.p_valid[j] = valid[src]; g.p_size[j] = ctype_size(p_ct[src]);
+                g.op_data[j] = out_data[k].p; g.op_valid[j] = out_has_valid[k] ? out_vbytes[k].as<uint8_t>() : nullptr;
+            }
+        }
+        if (n > 0 && n_match > 0) { join_probe_gather_kernel<<<grid_for(n), 256, 0, stream>>>(g); launches++; B200_CUDA(cudaGetLastError()); }
+        if (tail_flags.p) {
+            join_unmatched_flags_kernel<<<grid_for(n_build), 256, 0, stream>>>(d_bmatched.as<uint8_t>(), n_build, tail_flags.as<uint32_t>());
+            B200_CUDA(cudaMemsetAsync(tail_flags.as<uint32_t>() + n_build, 0, 4, stream));
+            launches++;
+            n_tail = scan.run(tail_flags.as<uint32_t>(), n_build + 1, tail_off.as<unsigned long long>(), stream, &launches);
+            tail_emitted = true;
+            if (n_tail > 0) {
+                // grow output columns, preserving the rows already gathered
+                for (int k = 0; k < n_out_cols; k++) {
+                    bool is_b = k < (int)kb.size();
+                    int src = is_b ? kb[k] : kp[k - kb.size()];
+                    size_t isz = ctype_size(is_b ? b_ct[src] : p_ct[src]);
+                    size_t need = (size_t)(n_match + n_tail + 32) * isz;
+                    if (need > out_data[k].bytes) {
+                        DevBuf nb; nb.alloc(need);
+                        B200_CUDA(cudaMemcpyAsync(nb.p, out_data[k].p, (size_t)n_match * isz, cudaMemcpyDeviceToDevice, stream));
+                        B200_CUDA(cudaStreamSynchronize(stream));
+                        out_data[k] = std::move(nb);
+                    }
+                    if (out_has_valid[k]) {
+                        size_t needv = (size_t)(n_match + n_tail) + 32;
+                        if (needv > out_vbytes[k].bytes) {
+                            DevBuf nb; nb.alloc(needv);
+                            B200_CUDA(cudaMemcpyAsync(nb.p, out_vbytes[k].p, (size_t)n_match, cudaMemcpyDeviceToDevice, stream));
+                            B200_CUDA(cudaStreamSynchronize(stream));
+                            out_vbytes[k] = std::move(nb);
+                        }
+                        out_bitmap[k].ensure((size_t)((n_match + n_tail + 31) / 32 + 1) * 4);
+                    }
+                }
+                TailArgs ta{};
+                ta.n_build = n_build; ta.flags = tail_flags.as<uint32_t>(); ta.off = tail_off.as<unsigned long long>();
+                ta.n_b = (int)kb.size(); ta.n_p = (int)kp.size();
+                for (int k = 0; k < n_out_cols; k++) {
+                    bool is_b = k < (int)kb.size();
+                    int src = is_b ? kb[k] : kp[k - kb.size()];
+                    size_t isz = ctype_size(is_b ? b_ct[src] : p_ct[src]);
+                    if (is_b) {
+                        ta.b_data[k] = bcol[src].buf.p; ta.b_valid[k] = b_has_valid[src] ? bvalid[src].buf.as<uint8_t>() : nullptr; ta.b_size[k] = (int)isz;
+                        ta.ob_data[k] = (char*)out_data[k].p + n_match * isz; ta.ob_valid[k] = out_has_valid[k] ? out_vbytes[k].as<uint8_t>() + n_match : nullptr;
+                    } else {
+                        int j = k - (int)kb.size();
+                        ta.p_size[j] = (int)isz;
+                        ta.op_data[j] = (char*)out_data[k].p + n_match * isz; ta.op_valid[j] = out_vbytes[k].as<uint8_t>() + n_match;
+                    }
+                }
+                join_unmatched_emit_kernel<<<grid_for(n_build), 256, 0, stream>>>(ta);
+                launches++;
+                B200_CUDA(cudaGetLastError());
+            }
+        }
+        int64_t rows = (int64_t)(n_match + n_tail);
+        for (int k = 0; k < n_out_cols; k++)
+            if (out_has_valid[k] && rows > 0) { pack_bitmap_kernel<<<grid_for(rows), 256, 0, stream>>>(out_vbytes[k].as<uint8_t>(), rows, out_bitmap[k].as<uint32_t>()); launches++; }
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaStreamSynchronize(stream));
+        describe_out(out, kb, kp, rows);
+        probe_rows += n; out_rows_total += rows;
+        return rows;
+    }
+};
+
+}  // namespace b200
+
+using b200::JoinState;
+
+extern "C" {
+
+void* b200_join_state_init(int64_t operator_id, const int8_t* build_arr_c_types, const int8_t* build_arr_array_types,
+                           int32_t n_build_arrs, const int8_t* probe_arr_c_types, const int8_t* probe_arr_array_types,
+                           int32_t n_probe_arrs, uint64_t n_keys, int32_t build_table_outer, int32_t probe_table_outer,
+                           int64_t output_batch_size, int32_t device, int64_t expected_build_rows, void* stream) {
+    (void)operator_id;
+    try {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw b200::Error("b200 join: no CUDA device available (this path has no CPU fallback)");
+        B200_REQUIRE(device >= 0 && device < ndev, "b200 join: bad device ordinal");
+        return new JoinState(build_arr_c_types, build_arr_array_types, n_build_arrs, probe_arr_c_types, probe_arr_array_types, n_probe_arrs,
+                             n_keys, build_table_outer != 0, probe_table_outer != 0, output_batch_size, device, expected_build_rows, (cudaStream_t)stream);
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return nullptr; }
+}
+
+int b200_join_build_consume_batch(void* state, const b200_table* in_table, int32_t is_last, int32_t* request_input) {
+    try {
+        B200_REQUIRE(state && in_table, "b200 join: null state or table");
+        ((JoinState*)state)->build_consume(in_table, is_last != 0);
+        if (request_input) *request_input = 1;
+        return is_last ? 1 : 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+int b200_join_probe_consume_batch(void* state, const b200_table* in_table, const uint64_t* kept_build_cols, int64_t n_kept_build,
+                                  const uint64_t* kept_probe_cols, int64_t n_kept_probe, b200_table* out, int64_t* total_rows,
+                                  int32_t is_last, int32_t* out_is_last) {
+    try {
+        B200_REQUIRE(state && in_table && out, "b200 join: null argument");
+        int64_t rows = ((JoinState*)state)->probe_consume(in_table, kept_build_cols, n_kept_build, kept_probe_cols, n_kept_probe, out, is_last != 0);
+        if (total_rows) *total_rows = rows;
+        if (out_is_last) *out_is_last = is_last ? 1 : 0;
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+void b200_delete_join_state(void* state) { delete (JoinState*)state; }
+
+int64_t b200_join_get_metric(void* state, int32_t which) {
+    auto* s = (JoinState*)state;
+    switch (which) {
+        case 0: return s->n_build;
+        case 1: return (int64_t)s->cap;
+        case 2: return s->probe_rows;
+        case 3: return s->out_rows_total;
+        case 4: return s->launches;
+        default: return -1;
+    }
+}
+
+}  // extern "C"

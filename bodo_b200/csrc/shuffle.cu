@@ -1,6 +1,269 @@
-// shuffle.cu — row -> rank radix partition (placeholder until the kernel lands; fails loudly).
+// shuffle.cu — row -> rank radix partition of a columnar table (sm_100a).
+//
+// Replaces hash_keys_table(SEED_HASH_PARTITION) + mpi_comm_info::set_send_count + fill_send_array of the
+// reference's shuffle_table (bodo/libs/_shuffle.cpp:94-163, 345-368, 477+, 1593-1642) and the
+// cudf::hash_partition + contiguous_split pair of its GPU path (bodo/libs/gpu_utils.cpp:96-123, 509-525).
+//
+// One stable counting-sort pass over the rows:
+//   K1 dest_hist   : dest[i] = (uint32) xxh3(key[i]) % n_pes (placement identical to the reference's
+//                    hash_to_rank), per-CTA histogram of its contiguous row tile  -> hist[cta][dest]
+//   K2 scan        : exclusive scan over (dest-major, cta-minor) -> first output row of every (cta, dest)
+//   K3 scatter     : every CTA re-walks its tile in row order; a warp-ballot multi-split gives each row its
+//                    stable rank; ALL columns are scattered in the same pass (no contiguous_split copy)
+//   K4 pack bitmap : validity bytes of each destination segment are re-packed into a per-destination Arrow
+//                    bitmap that starts on a byte boundary (the reference sends one null-bitmap buffer per
+//                    destination with byte padding, _shuffle.cpp:661-875).
+// Rows keep their input order inside a destination (fill_send_array is stable too), so the result is
+// bit-identical to the oracle's oracle_shuffle_partition.
+#include <vector>
+
 #include "common.cuh"
-extern "C" {
-int b200_hash_to_rank(const b200_table*, int32_t, int32_t*, void*) { b200::set_last_error("b200_hash_to_rank: not implemented yet"); return -1; }
-int b200_shuffle_partition(const b200_table*, int64_t, int32_t, b200_table*, int64_t*, void*) { b200::set_last_error("b200_shuffle_partition: not implemented yet"); return -1; }
+
+namespace b200 {
+
+constexpr int PART_THREADS = 256;
+constexpr int MAX_PES = 256;
+constexpr int MAX_SHUFFLE_COLS = 32;
+
+__device__ __forceinline__ uint32_t row_hash32(const void* key_data, int key_ctype, const uint8_t* key_valid, int64_t i) {
+    if (!bit_valid(key_valid, i)) return (uint32_t)xxh3_64_short(1ull, 8, SEED_HASH_PARTITION);  // hash_na_val
+    if (ctype_size(key_ctype) == 8) return (uint32_t)xxh3_64_short((uint64_t)load_int_as_i64(key_data, key_ctype, i), 8, SEED_HASH_PARTITION);
+    // 4-byte keys hash their 4 raw bytes (hash_inner_32<T> uses sizeof(T))
+    return (uint32_t)xxh3_64_short((uint64_t)(uint32_t)load_int_as_i64(key_data, key_ctype, i), 4, SEED_HASH_PARTITION);
 }
+
+__global__ void hash_to_rank_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid, int64_t n, int n_pes,
+                                    int32_t* dest) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride)
+        dest[i] = hash_to_rank_u32(row_hash32(key_data, key_ctype, key_valid, i), n_pes);
+}
+
+// K1: tile = contiguous rows [cta * tile_rows, ...). dest8 holds the destination of every row.
+__global__ void __launch_bounds__(PART_THREADS) dest_hist_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid,
+                                                                 int64_t n, int64_t tile_rows, int n_pes, uint8_t* dest8,
+                                                                 unsigned int* hist /* [gridDim.x][n_pes] */) {
+    __shared__ unsigned int sh[MAX_PES];
+    for (int d = threadIdx.x; d < n_pes; d += blockDim.x) sh[d] = 0;
+    __syncthreads();
+    int64_t r0 = (int64_t)blockIdx.x * tile_rows;
+    int64_t r1 = r0 + tile_rows < n ? r0 + tile_rows : n;
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+        int d = hash_to_rank_u32(row_hash32(key_data, key_ctype, key_valid, i), n_pes);
+        dest8[i] = (uint8_t)d;
+        atomicAdd(&sh[d], 1u);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < n_pes; d += blockDim.x) hist[(size_t)blockIdx.x * n_pes + d] = sh[d];
+}
+
+// K2: one CTA. offsets[cta][d] = sum_{d' < d} total[d'] + sum_{cta' < cta} hist[cta'][d]; totals[d] = rows per dest.
+__global__ void scan_hist_kernel(const unsigned int* hist, int n_ctas, int n_pes, long long* offsets, long long* totals) {
+    __shared__ long long tot[MAX_PES];
+    for (int d = threadIdx.x; d < n_pes; d += blockDim.x) {
+        long long s = 0;
+        for (int c = 0; c < n_ctas; c++) s += hist[(size_t)c * n_pes + d];
+        tot[d] = s;
+        totals[d] = s;
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < n_pes; d += blockDim.x) {
+        long long base = 0;
+        for (int e = 0; e < d; e++) base += tot[e];
+        for (int c = 0; c < n_ctas; c++) {
+            offsets[(size_t)c * n_pes + d] = base;
+            base += hist[(size_t)c * n_pes + d];
+        }
+    }
+}
+
+struct ScatterArgs {
+    int64_t n;
+    int64_t tile_rows;
+    int n_pes;
+    int n_cols;
+    const uint8_t* dest8;
+    const long long* offsets;  // [n_ctas][n_pes]
+    const void* in_data[MAX_SHUFFLE_COLS];
+    const uint8_t* in_valid[MAX_SHUFFLE_COLS];
+    void* out_data[MAX_SHUFFLE_COLS];
+    uint8_t* out_valid_bytes[MAX_SHUFFLE_COLS];  // one byte per row (temp), nullptr if the column has no bitmap
+    int itemsize[MAX_SHUFFLE_COLS];
+    long long* perm_out;  // optional: source row of every output row (tests), may be nullptr
+};
+
+// K3: stable multi-split. Per 256-row chunk: rank inside the warp via __match_any_sync, across warps via a
+// [warps][n_pes] count matrix in shared memory.
+__global__ void __launch_bounds__(PART_THREADS) scatter_kernel(const __grid_constant__ ScatterArgs a) {
+    constexpr int NW = PART_THREADS / 32;
+    __shared__ long long run[MAX_PES];        // next output row per destination for this CTA
+    __shared__ unsigned int wcnt[NW][MAX_PES];  // rows of dest d in warp w of the current chunk
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = threadIdx.x; d < a.n_pes; d += blockDim.x) run[d] = a.offsets[(size_t)blockIdx.x * a.n_pes + d];
+    int64_t r0 = (int64_t)blockIdx.x * a.tile_rows;
+    int64_t r1 = r0 + a.tile_rows < a.n ? r0 + a.tile_rows : a.n;
+    for (int64_t c0 = r0; c0 < r1; c0 += PART_THREADS) {
+        for (int j = threadIdx.x; j < NW * MAX_PES; j += blockDim.x) (&wcnt[0][0])[j] = 0;
+        __syncthreads();
+        int64_t i = c0 + threadIdx.x;
+        bool in = i < r1;
+        int d = in ? (int)a.dest8[i] : -1;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int rank_in_warp = __popc(peers & ((1u << lane) - 1));
+        if (in && rank_in_warp == 0) wcnt[warp][d] = __popc(peers);
+        __syncthreads();
+        long long pos = 0;
+        if (in) {
+            unsigned before = 0;
+            for (int w = 0; w < warp; w++) before += wcnt[w][d];
+            pos = run[d] + before + rank_in_warp;
+        }
+        __syncthreads();
+        // advance the per-destination cursors by this chunk's totals
+        for (int e = threadIdx.x; e < a.n_pes; e += blockDim.x) {
+            unsigned t = 0;
+            for (int w = 0; w < NW; w++) t += wcnt[w][e];
+            run[e] += t;
+        }
+        if (in) {
+            if (a.perm_out) a.perm_out[pos] = i;
+            for (int c = 0; c < a.n_cols; c++) {
+                switch (a.itemsize[c]) {
+                    case 8: ((uint64_t*)a.out_data[c])[pos] = ((const uint64_t*)a.in_data[c])[i]; break;
+                    case 4: ((uint32_t*)a.out_data[c])[pos] = ((const uint32_t*)a.in_data[c])[i]; break;
+                    case 2: ((uint16_t*)a.out_data[c])[pos] = ((const uint16_t*)a.in_data[c])[i]; break;
+                    default: ((uint8_t*)a.out_data[c])[pos] = ((const uint8_t*)a.in_data[c])[i]; break;
+                }
+                if (a.out_valid_bytes[c]) a.out_valid_bytes[c][pos] = bit_valid(a.in_valid[c], i) ? 1 : 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// K4: one thread per output bitmap byte of a destination segment.
+__global__ void pack_segment_bitmaps_kernel(const uint8_t* valid_bytes, const long long* totals, int n_pes, uint8_t* out_bitmap) {
+    // segment d: rows [row_off[d], row_off[d] + totals[d]) -> bytes [byte_off[d], byte_off[d] + ceil(totals[d] / 8))
+    long long row_off = 0, byte_off = 0;
+    for (int d = 0; d < n_pes; d++) {
+        long long cnt = totals[d];
+        long long nbytes = (cnt + 7) >> 3;
+        for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < nbytes; b += (long long)gridDim.x * blockDim.x) {
+            unsigned v = 0;
+            for (int k = 0; k < 8; k++) {
+                long long r = b * 8 + k;
+                if (r < cnt && valid_bytes[row_off + r]) v |= 1u << k;
+            }
+            out_bitmap[byte_off + b] = (uint8_t)v;
+        }
+        row_off += cnt;
+        byte_off += nbytes;
+    }
+}
+
+struct StreamBuf {  // stream-ordered scratch allocation
+    void* p = nullptr;
+    cudaStream_t s;
+    StreamBuf(size_t n, cudaStream_t st) : s(st) { B200_CUDA(cudaMallocAsync(&p, n ? n : 8, st)); }
+    ~StreamBuf() { if (p) cudaFreeAsync(p, s); }
+    template <typename T> T* as() { return (T*)p; }
+};
+
+static int table_device(const b200_table* t) {
+    B200_REQUIRE(t->device >= 0, "b200 shuffle: the table must be device resident");
+    return t->device;
+}
+
+void shuffle_partition(const b200_table* in, int64_t n_keys, int n_pes, b200_table* out, int64_t* send_counts,
+                       long long* perm_out_dev, cudaStream_t st) {
+    B200_REQUIRE(n_keys == 1, "b200 shuffle: exactly one key column is supported");
+    B200_REQUIRE(n_pes >= 1 && n_pes <= MAX_PES, "b200 shuffle: n_pes must be in [1, 256]");
+    B200_REQUIRE(in->n_cols >= 1 && in->n_cols <= MAX_SHUFFLE_COLS, "b200 shuffle: between 1 and 32 columns are supported");
+    B200_REQUIRE(out->n_cols == in->n_cols, "b200 shuffle: out table must have the same number of columns");
+    int dev = table_device(in);
+    B200_CUDA(cudaSetDevice(dev));
+    int64_t n = in->n_rows;
+    int kct = in->cols[0].c_type;
+    B200_REQUIRE((ctype_size(kct) == 4 || ctype_size(kct) == 8) && !ctype_is_float(kct), "b200 shuffle: key must be a 4- or 8-byte integer/date column");
+    for (int d = 0; d < n_pes; d++) send_counts[d] = 0;
+    out->n_rows = n;
+    if (n == 0) return;
+    int sms = num_sms(dev);
+    int n_ctas = (int)std::min<int64_t>((int64_t)sms * 8, (n + PART_THREADS - 1) / PART_THREADS);
+    int64_t tile_rows = ((n + n_ctas - 1) / n_ctas + PART_THREADS - 1) / PART_THREADS * PART_THREADS;
+    n_ctas = (int)((n + tile_rows - 1) / tile_rows);
+    StreamBuf dest8((size_t)n, st), hist((size_t)n_ctas * n_pes * 4, st), offsets((size_t)n_ctas * n_pes * 8, st), totals((size_t)n_pes * 8, st);
+    dest_hist_kernel<<<n_ctas, PART_THREADS, 0, st>>>(in->cols[0].data, kct, in->cols[0].validity, n, tile_rows, n_pes,
+                                                      dest8.as<uint8_t>(), hist.as<unsigned int>());
+    B200_CUDA(cudaGetLastError());
+    scan_hist_kernel<<<1, 256, 0, st>>>(hist.as<unsigned int>(), n_ctas, n_pes, offsets.as<long long>(), totals.as<long long>());
+    B200_CUDA(cudaGetLastError());
+    ScatterArgs a{};
+    a.n = n; a.tile_rows = tile_rows; a.n_pes = n_pes; a.n_cols = in->n_cols; a.dest8 = dest8.as<uint8_t>();
+    a.offsets = offsets.as<long long>(); a.perm_out = perm_out_dev;
+    std::vector<StreamBuf*> vbytes(in->n_cols, nullptr);
+    for (int c = 0; c < in->n_cols; c++) {
+        const b200_column& ic = in->cols[c];
+        b200_column& oc = out->cols[c];
+        B200_REQUIRE(ctype_size(ic.c_type) > 0, "b200 shuffle: unsupported column dtype");
+        B200_REQUIRE(oc.data != nullptr, "b200 shuffle: out column data pointer is null");
+        a.in_data[c] = ic.data; a.in_valid[c] = ic.validity; a.out_data[c] = oc.data; a.itemsize[c] = ctype_size(ic.c_type);
+        a.out_valid_bytes[c] = nullptr;
+        if (ic.validity) {
+            B200_REQUIRE(oc.validity != nullptr, "b200 shuffle: out column needs a validity buffer of ceil(n/8) + n_pes bytes");
+            vbytes[c] = new StreamBuf((size_t)n, st);
+            a.out_valid_bytes[c] = vbytes[c]->as<uint8_t>();
+        }
+        oc.length = n; oc.c_type = ic.c_type; oc.arr_type = ic.arr_type;
+    }
+    scatter_kernel<<<n_ctas, PART_THREADS, 0, st>>>(a);
+    B200_CUDA(cudaGetLastError());
+    for (int c = 0; c < in->n_cols; c++) {
+        if (!vbytes[c]) continue;
+        pack_segment_bitmaps_kernel<<<sms * 4, 256, 0, st>>>(vbytes[c]->as<uint8_t>(), totals.as<long long>(), n_pes, out->cols[c].validity);
+        delete vbytes[c];
+    }
+    B200_CUDA(cudaGetLastError());
+    std::vector<long long> h(n_pes);
+    B200_CUDA(cudaMemcpyAsync(h.data(), totals.p, (size_t)n_pes * 8, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    for (int d = 0; d < n_pes; d++) send_counts[d] = h[d];
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int b200_hash_to_rank(const b200_table* in_table, int32_t n_pes, int32_t* dest_out, void* stream) {
+    try {
+        B200_REQUIRE(in_table && in_table->n_cols >= 1 && n_pes >= 1, "b200_hash_to_rank: bad arguments");
+        int dev = b200::table_device(in_table);
+        B200_CUDA(cudaSetDevice(dev));
+        if (in_table->n_rows == 0) return 0;
+        const b200_column& k = in_table->cols[0];
+        B200_REQUIRE((b200::ctype_size(k.c_type) == 4 || b200::ctype_size(k.c_type) == 8) && !b200::ctype_is_float(k.c_type), "b200_hash_to_rank: key must be a 4- or 8-byte integer/date column");
+        b200::hash_to_rank_kernel<<<b200::num_sms(dev) * 8, 256, 0, (cudaStream_t)stream>>>(k.data, k.c_type, k.validity, in_table->n_rows, n_pes, dest_out);
+        B200_CUDA(cudaGetLastError());
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+int b200_shuffle_partition(const b200_table* in_table, int64_t n_keys, int32_t n_pes, b200_table* out, int64_t* send_counts,
+                           void* stream) {
+    try {
+        B200_REQUIRE(in_table && out && send_counts, "b200_shuffle_partition: null argument");
+        b200::shuffle_partition(in_table, n_keys, n_pes, out, send_counts, nullptr, (cudaStream_t)stream);
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+int b200_shuffle_partition_perm(const b200_table* in_table, int64_t n_keys, int32_t n_pes, b200_table* out, int64_t* send_counts,
+                                int64_t* perm_out_dev, void* stream) {
+    try {
+        B200_REQUIRE(in_table && out && send_counts, "b200_shuffle_partition_perm: null argument");
+        b200::shuffle_partition(in_table, n_keys, n_pes, out, send_counts, (long long*)perm_out_dev, (cudaStream_t)stream);
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+"""Streaming hash join operator API — the host-side mirror of bodo/libs/streaming/join.py.
+
+Same verbs and calling protocol as the reference (init_join_state :991-1100, join_build_consume_batch
+:1270-1330, join_probe_consume_batch :1838-1950, delete_join_state :1959), so the reference's streaming join
+test loops (bodo/tests/test_streaming/test_join.py) carry over.  The work happens in libbodo_b200.so.
+
+Output column order is the reference's: kept build-table columns first, then kept probe-table columns
+(both in logical input order, the key column included on each side unless dropped through used/kept cols).
+"""
+
+from __future__ import annotations
+
+from .. import _lib
+from .._lib import ffi
+from ..table import CTable, Table, table_from_ctable
+
+
+class JoinState:
+    def __init__(self, operator_id, build_key_inds, probe_key_inds, build_colnames, probe_colnames, build_outer, probe_outer,
+                 output_batch_size, expected_build_rows, device, stream):
+        self.operator_id = int(operator_id)
+        self.build_key_inds = tuple(int(k) for k in build_key_inds)
+        self.probe_key_inds = tuple(int(k) for k in probe_key_inds)
+        if len(self.build_key_inds) != 1 or len(self.probe_key_inds) != 1:
+            raise _lib.B200Error("Streaming Join: exactly one equi-join key per side is supported")
+        self.build_colnames = list(build_colnames) if build_colnames is not None else None
+        self.probe_colnames = list(probe_colnames) if probe_colnames is not None else None
+        self.build_outer = bool(build_outer)
+        self.probe_outer = bool(probe_outer)
+        self.output_batch_size = int(output_batch_size)
+        self.expected_build_rows = int(expected_build_rows)
+        self.device = device
+        self.stream = int(stream)
+        self.handle = None
+        self.build_schema = None  # (c_types, arr_types) of the physical (keys-first) build table
+        self.build_indices = None
+        self.probe_indices = None
+        self.build_names = None
+        self._pending_build = []
+        self._out = None
+
+    def _physical(self, table: Table, key_inds):
+        others = [i for i in range(table.n_cols) if i not in key_inds]
+        return list(key_inds) + others
+
+    def _init_c(self, probe: Table):
+        L = _lib.lib()
+        _lib.require_gpu()
+        bct, bat = self.build_schema
+        self.probe_indices = self._physical(probe, self.probe_key_inds)
+        pcols = [probe.columns[i] for i in self.probe_indices]
+        if self.device is None:
+            import torch
+
+            self.device = probe.device if probe.device >= 0 else torch.cuda.current_device()
+        h = L.b200_join_state_init(self.operator_id, ffi.new("int8_t[]", bct), ffi.new("int8_t[]", bat), len(bct),
+                                   ffi.new("int8_t[]", [c.c_type for c in pcols]), ffi.new("int8_t[]", [c.arr_type for c in pcols]),
+                                   len(pcols), 1, int(self.build_outer), int(self.probe_outer), self.output_batch_size, self.device,
+                                   self.expected_build_rows, ffi.cast("void*", self.stream))
+        self.handle = _lib.check_ptr(h, "init_join_state")
+
+
+def init_join_state(operator_id, build_key_inds, probe_key_inds, build_colnames, probe_colnames, build_outer, probe_outer,
+                    interval_build_columns=None, force_broadcast=False, op_pool_size_bytes=-1, non_equi_condition=None,
+                    build_parallel=False, probe_parallel=False, *, output_batch_size=32768, expected_build_rows=0, device=None,
+                    stream=0) -> JoinState:
+    """Mirror of bodo.libs.streaming.join.init_join_state (join.py:991-1100).  Interval joins, broadcast forcing and
+    non-equi conditions are out of scope and must be left at their defaults."""
+    if interval_build_columns not in (None, (), []) or non_equi_condition is not None:
+        raise _lib.B200Error("Streaming Join: interval / non-equi joins are not supported by bodo_b200")
+    g = lambda x: getattr(x, "meta", x)
+    return JoinState(operator_id, g(build_key_inds), g(probe_key_inds), g(build_colnames), g(probe_colnames), build_outer,
+                     probe_outer, output_batch_size, expected_build_rows, device, stream)
+
+
+def join_build_consume_batch(join_state: JoinState, table: Table, is_last: bool):
+    """Mirror of join_build_consume_batch (join.py:1270-1330): returns (is_last, request_input)."""
+    st = join_state
+    if st.build_indices is None:
+        st.build_indices = st._physical(table, st.build_key_inds)
+        cols = [table.columns[i] for i in st.build_indices]
+        st.build_schema = ([c.c_type for c in cols], [c.arr_type for c in cols])
+        st.build_names = [table.names[i] for i in st.build_indices]
+    phys = table.select(st.build_indices)
+    if st.handle is None:
+        # the C state needs both schemas; build batches that arrive before the first probe batch are parked
+        st._pending_build.append((phys, bool(is_last)))
+        return bool(is_last), True
+    return _feed_build(st, phys, is_last), True
+
+
+def _feed_build(st: JoinState, phys: Table, is_last: bool) -> bool:
+    L = _lib.lib()
+    ct = CTable(phys)
+    req = ffi.new("int32_t*")
+    rc = _lib.check(L.b200_join_build_consume_batch(st.handle, ct.ptr, int(bool(is_last)), req), "join_build_consume_batch")
+    return bool(rc)
+
+
+def join_probe_consume_batch(join_state: JoinState, table: Table, is_last: bool, produce_output: bool = True, used_cols=None):
+    """Mirror of join_probe_consume_batch (join.py:1838-1950): returns (out_table, is_last, request_input).
+    used_cols = (kept_build_cols, kept_probe_cols) as logical column indices, or None to keep everything."""
+    st = join_state
+    L = _lib.lib()
+    if st.build_indices is None:
+        raise _lib.B200Error("join_probe_consume_batch called before any build batch")
+    if st.handle is None:
+        st._init_c(table)
+        pend, st._pending_build = st._pending_build, []
+        for phys, last in pend:
+            _feed_build(st, phys, last)
+    phys = table.select(st.probe_indices)
+    if used_cols is None:
+        kb_logical = sorted(st.build_indices)
+        kp_logical = sorted(st.probe_indices)
+    else:
+        kb_logical, kp_logical = list(used_cols[0]), list(used_cols[1])
+    kb = [st.build_indices.index(i) for i in kb_logical]
+    kp = [st.probe_indices.index(i) for i in kp_logical]
+    names = [st.build_names[j] for j in kb] + [phys.names[j] for j in kp]
+    # unique output names (a key named the same on both sides appears twice, like pandas' _x/_y without renaming)
+    seen, uniq = set(), []
+    for nm in names:
+        cand, k = nm, 1
+        while cand in seen:
+            cand = f"{nm}_{k}"; k += 1
+        seen.add(cand); uniq.append(cand)
+    ct = CTable(phys)
+    ncols = len(kb) + len(kp)
+    st._out_cols = ffi.new("b200_column[]", max(ncols, 1))
+    st._out = ffi.new("b200_table*")
+    st._out.cols = st._out_cols
+    total = ffi.new("int64_t*")
+    out_last = ffi.new("int32_t*")
+    _lib.check(L.b200_join_probe_consume_batch(st.handle, ct.ptr, ffi.new("uint64_t[]", kb or [0]), len(kb),
+                                               ffi.new("uint64_t[]", kp or [0]), len(kp), st._out, total, int(bool(is_last)), out_last),
+               "join_probe_consume_batch")
+    out = table_from_ctable(st._out, ncols, uniq, owner=st)
+    return out, bool(out_last[0]), True
+
+
+def delete_join_state(join_state: JoinState) -> None:
+    if join_state.handle is not None:
+        _lib.lib().b200_delete_join_state(join_state.handle)
+        join_state.handle = None
+
+
+def get_metric(join_state: JoinState, which: int) -> int:
+    return int(_lib.lib().b200_join_get_metric(join_state.handle, which))

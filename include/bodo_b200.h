@@ -155,6 +155,11 @@ int b200_hash_to_rank(const b200_table* in_table, int32_t n_pes, int32_t* dest_o
  * (segment d starts at byte offset of a fresh bitmap: see DESIGN.md). */
 int b200_shuffle_partition(const b200_table* in_table, int64_t n_keys, int32_t n_pes,
                            b200_table* out, int64_t* send_counts, void* stream);
+/* Same, and also writes the source row of every output row to perm_out_dev (device int64[n_rows]);
+ * used by the parity tests to compare the placement with the oracle row by row. */
+int b200_shuffle_partition_perm(const b200_table* in_table, int64_t n_keys, int32_t n_pes,
+                                b200_table* out, int64_t* send_counts, int64_t* perm_out_dev,
+                                void* stream);
 
 /* ---- helpers for host code that does not link CUDA ---- */
 void* b200_device_malloc(int32_t device, int64_t nbytes);

@@ -1,0 +1,130 @@
+"""GPU parity tests for the streaming hash join: row-set equality under sort against the CPU oracle and pandas
+(join output order is unspecified in the reference as well; its tests sort before comparing)."""
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from bodo_b200.streaming.join import (delete_join_state, init_join_state, join_build_consume_batch,
+                                      join_probe_consume_batch)
+from bodo_b200.table import Table
+from tests.helpers import table_to_device
+
+pytestmark = pytest.mark.gpu
+
+
+def stream_join(build_df, probe_df, build_outer=False, probe_outer=False, batch_size=None, to_device=False, used_cols=None):
+    """Reference-shaped streaming loop (bodo/tests/test_streaming/test_join.py): build batches, then probe batches."""
+    bt, pt = Table.from_pandas(build_df), Table.from_pandas(probe_df)
+    st = init_join_state(-1, (0,), (0,), tuple(build_df.columns), tuple(probe_df.columns), build_outer, probe_outer)
+    bs = batch_size or max(bt.n_rows, pt.n_rows, 1)
+    it, last = 0, False
+    while not last:
+        b = bt.slice(it * bs, (it + 1) * bs)
+        last = (it + 1) * bs >= bt.n_rows
+        it += 1
+        join_build_consume_batch(st, table_to_device(b) if to_device else b, last)
+    outs, it, last = [], 0, False
+    while not last:
+        p = pt.slice(it * bs, (it + 1) * bs)
+        last = (it + 1) * bs >= pt.n_rows
+        it += 1
+        out, out_last, _ = join_probe_consume_batch(st, table_to_device(p) if to_device else p, last, True, used_cols)
+        outs.append(out.to_pandas())
+    delete_join_state(st)
+    return pd.concat(outs, ignore_index=True)
+
+
+def oracle_join_frame(oracle, build_df, probe_df, build_outer=False, probe_outer=False):
+    def kv(s):
+        if hasattr(s.array, "_mask"):
+            return np.asarray(s.array._data, dtype=np.int64), ~np.asarray(s.array._mask)
+        return s.to_numpy(dtype=np.int64), None
+    bk, bv = kv(build_df.iloc[:, 0])
+    pk, pv = kv(probe_df.iloc[:, 0])
+    bi, pi = oracle.hash_join(bk, bv, pk, pv, build_outer, probe_outer, True)
+    out = {}
+    for name in build_df.columns:
+        col = build_df[name].astype("Float64" if build_df[name].dtype.kind == "f" else "Int64")
+        vals = col.take(np.where(bi >= 0, bi, 0)).reset_index(drop=True)
+        vals[bi < 0] = pd.NA
+        out[f"b_{name}"] = vals
+    for name in probe_df.columns:
+        col = probe_df[name].astype("Float64" if probe_df[name].dtype.kind == "f" else "Int64")
+        vals = col.take(np.where(pi >= 0, pi, 0)).reset_index(drop=True)
+        vals[pi < 0] = pd.NA
+        out[f"p_{name}"] = vals
+    return pd.DataFrame(out)
+
+
+def canon(df):
+    df = df.copy()
+    df.columns = [f"c{i}" for i in range(df.shape[1])]
+    for c in df.columns:
+        df[c] = df[c].to_numpy(dtype="float64", na_value=np.nan)
+    return df.sort_values(list(df.columns), na_position="last").reset_index(drop=True)
+
+
+def assert_rowset_equal(got, exp):
+    g, e = canon(got), canon(exp)
+    assert g.shape == e.shape, (g.shape, e.shape)
+    np.testing.assert_array_equal(g.to_numpy(), e.to_numpy())
+
+
+@pytest.mark.parametrize("build_outer,probe_outer", [(False, False), (True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("to_device", [False, True])
+def test_hash_join_non_nullable_outer_fixture(gpu_lib, oracle, build_outer, probe_outer, to_device):
+    # fixture of test_hash_join_non_nullable_outer (bodo/tests/test_streaming/test_join.py:922-940):
+    # many-to-many duplicates (key 2 -> 25 x 25 rows), unmatched keys on both sides
+    df1 = pd.DataFrame({"A": [1, 2, 3, 4, 5] * 25, "B": np.array([1, 2, 3, 4, 5] * 25, dtype=np.int32)})
+    df2 = pd.DataFrame({"C": [2, 6] * 25, "D": np.array([2, 6] * 25, dtype=np.int8)})
+    got = stream_join(df1, df2, build_outer, probe_outer, batch_size=40, to_device=to_device)
+    exp = oracle_join_frame(oracle, df1, df2, build_outer, probe_outer)
+    assert_rowset_equal(got, exp)
+    how = {(False, False): "inner", (True, True): "outer", (True, False): "left", (False, True): "right"}[(build_outer, probe_outer)]
+    pexp = df1.merge(df2, left_on="A", right_on="C", how=how)
+    assert_rowset_equal(got, pexp)
+
+
+def test_shuffle_batching_fixture(gpu_lib):
+    # test_shuffle_batching (bodo/tests/test_streaming/test_join.py:4803-4816): 60 000-row 1:1 join
+    build = pd.DataFrame({"A": np.arange(60000), "B": [1, 2, 3, 4, 5, 6] * 10000})
+    probe = pd.DataFrame({"C": np.arange(60000), "D": [1, 2, 3, 4, 5, 6] * 10000})
+    got = stream_join(build, probe, batch_size=4096)
+    exp = pd.DataFrame({"A": np.arange(60000), "B": [1, 2, 3, 4, 5, 6] * 10000, "C": np.arange(60000), "D": [1, 2, 3, 4, 5, 6] * 10000})
+    assert_rowset_equal(got, exp)
+
+
+@pytest.mark.parametrize("how", ["inner", "left", "right", "outer"])
+def test_merge_nullable_keys(gpu_lib, how):
+    # test_merge fixture (bodo/tests/test_df_lib/test_end_to_end.py:1255-1286): nullable Int64 keys [2,2,3] vs [2,3,8];
+    # NA keys match NA keys (pandas semantics)
+    left = pd.DataFrame({"A": pd.array([2, 2, 3, None, None], dtype="Int64"), "B": [1.5, 2.5, 3.5, 4.5, 5.5]})
+    right = pd.DataFrame({"C": pd.array([2, 3, 8, None], dtype="Int64"), "D": pd.array([10, None, 30, 40], dtype="Int64")})
+    # reference convention: right table = build side
+    bo, po = {"inner": (False, False), "left": (False, True), "right": (True, False), "outer": (True, True)}[how]
+    got = stream_join(right, left, bo, po, batch_size=2)
+    exp = right.merge(left, left_on="C", right_on="A", how={"left": "right", "right": "left"}.get(how, how))
+    assert_rowset_equal(got, exp)
+
+
+def test_empty_sides(gpu_lib):
+    b = pd.DataFrame({"A": np.array([], dtype=np.int64), "B": np.array([], dtype=np.float64)})
+    p = pd.DataFrame({"C": np.arange(10, dtype=np.int64), "D": np.arange(10, dtype=np.float64)})
+    assert len(stream_join(b, p)) == 0
+    assert len(stream_join(b, p, probe_outer=True)) == 10
+    assert len(stream_join(p, b)) == 0
+    assert len(stream_join(p, b, build_outer=True)) == 10
+
+
+def test_synthetic_join_vs_oracle(gpu_lib, oracle):
+    rng = np.random.default_rng(5)
+    nb, npr = 200_000, 1_000_000
+    build = pd.DataFrame({"k": rng.permutation(nb).astype(np.int64), "b1": rng.integers(0, 1 << 40, nb), "b2": rng.random(nb)})
+    probe = pd.DataFrame({"k": rng.integers(0, nb * 2, npr).astype(np.int64), "p1": rng.integers(0, 1 << 40, npr), "p2": rng.random(npr)})
+    got = stream_join(build, probe, batch_size=300_000, to_device=True)
+    exp = oracle_join_frame(oracle, build, probe)
+    assert_rowset_equal(got, exp)
+    # kept columns: drop the probe key and b2
+    got2 = stream_join(build, probe, batch_size=300_000, to_device=True, used_cols=([0, 1], [1, 2]))
+    assert_rowset_equal(got2, exp.iloc[:, [0, 1, 4, 5]])
