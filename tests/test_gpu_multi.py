@@ -1,0 +1,93 @@
+"""Multi-GPU (NCCL) parity tests: sharded groupby with the partial-aggregate exchange and shuffle_table over
+all-to-all-v.  Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import pandas as pd
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from bodo_b200.shuffle import shuffle_table
+        from bodo_b200.streaming.groupby import (delete_groupby_state, groupby_build_consume_batch,
+                                                 groupby_produce_output_batch, init_groupby_state)
+        from bodo_b200.table import Table
+        from oracle import oracle as O
+        from tests.helpers import table_to_device
+        n_total, n_groups = 600_000, 20_000
+        k, v = O.synth_fill(0, n_total, n_groups, 21)
+        vf = (v.astype(np.float64) + 0.25)
+        chunk = (n_total + world - 1) // world
+        lo, hi = rank * chunk, min(n_total, (rank + 1) * chunk)
+        df = pd.DataFrame({"k": k[lo:hi], "v": v[lo:hi], "f": vf[lo:hi]})
+        t = table_to_device(Table.from_pandas(df), rank)
+        # --- sharded groupby: consume local rows in 3 batches, exchange on the last one ---
+        fn = ("sum", "count", "mean", "min", "max")
+        st = init_groupby_state(-1, (0,), fn, (0, 1, 2, 3, 4, 5), (1, 1, 2, 1, 2), parallel=True, expected_groups=64, device=rank,
+                                output_batch_size=1 << 30)
+        nloc = hi - lo
+        cuts = [0, nloc // 3, 2 * nloc // 3, nloc]
+        host = Table.from_pandas(df)
+        for b in range(3):
+            groupby_build_consume_batch(st, table_to_device(host.slice(cuts[b], cuts[b + 1]), rank), b == 2, True)
+        out, last = groupby_produce_output_batch(st, True)
+        got = out.to_pandas()
+        delete_groupby_state(st)
+        exp = O.groupby(k, None, list(fn), [v, v, vf, v, vf], n_pes=world, rank=rank)
+        e = pd.DataFrame({"k": exp["keys"], **{f"f{j}": c[0] for j, c in enumerate(exp["cols"])}}).sort_values("k").reset_index(drop=True)
+        got.columns = ["k"] + [f"f{j}" for j in range(5)]
+        g = got.sort_values("k").reset_index(drop=True)
+        ok_keys = bool(len(g) == len(e) and (g.k.to_numpy() == e.k.to_numpy()).all())
+        ok_int = ok_keys and all((g[c].to_numpy() == e[c].to_numpy()).all() for c in ("f0", "f1", "f3"))
+        ok_flt = ok_keys and all(np.allclose(g[c].to_numpy(dtype=float), e[c].to_numpy(dtype=float), rtol=1e-5, atol=1e-8) for c in ("f2", "f4"))
+        # --- shuffle_table over NCCL: rows land on hash_to_rank(key), nothing lost ---
+        sh = shuffle_table(t, 1, True)
+        sdf = sh.to_pandas()
+        dest = O.hash_to_rank(sdf["k"].to_numpy(), None, world)
+        ok_owner = bool((dest == rank).all())
+        tot = torch.tensor([len(sdf), int(sdf["v"].sum()), nloc, int(df["v"].sum())], dtype=torch.int64, device=f"cuda:{rank}")
+        dist.all_reduce(tot)
+        ok_cons = tot[0].item() == tot[2].item() and tot[1].item() == tot[3].item()
+        q.put((rank, ok_keys, ok_int, ok_flt, ok_owner, ok_cons))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_groupby_and_shuffle_nccl(gpu_lib):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for r in sorted(res, key=lambda x: x[0]):
+        assert len(r) == 6 and all(r[1:]), r
