@@ -49,7 +49,10 @@ struct ConsumeArgs {
     OpDesc ops[MAX_OPS];
 };
 
-// find-or-insert; returns slot or UINT64_MAX when the table is at its group limit
+// find-or-insert with linear probing over 8-byte key slots; returns the slot, or UINT64_MAX when the table is at
+// its group limit (group_limit < 0 disables the limit: rehash into a table that is known to be large enough).
+// Measured on B200 (scratch/ubench2.cu, profiles/r01_ubench2.txt): a 4-key bucket fetched with one 256-bit load
+// is SLOWER than this (29 vs 40 Grows/s) — L2 random-request rate, not probe-chain latency, is the limit.
 __device__ __forceinline__ uint64_t find_or_insert(long long* __restrict__ tkeys, uint64_t cap, long long key,
                                                    long long* counters, long long group_limit) {
     uint64_t mask = cap - 1;
@@ -59,15 +62,17 @@ __device__ __forceinline__ uint64_t find_or_insert(long long* __restrict__ tkeys
         if (k == key) return s;
         if (k == EMPTY_KEY) {
             // take a ticket first so the table can never exceed group_limit (probing always terminates)
-            long long t = atomicAdd((unsigned long long*)&counters[0], 1ull);
-            if (t >= group_limit) {
-                atomicAdd((unsigned long long*)&counters[0], (unsigned long long)-1ll);
-                return ~0ull;
+            if (group_limit >= 0) {
+                long long t = atomicAdd((unsigned long long*)&counters[0], 1ull);
+                if (t >= group_limit) {
+                    atomicAdd((unsigned long long*)&counters[0], (unsigned long long)-1ll);
+                    return ~0ull;
+                }
             }
             long long prev = atomicCAS((unsigned long long*)(tkeys + s), (unsigned long long)EMPTY_KEY,
                                        (unsigned long long)key);
             if (prev == EMPTY_KEY) return s;
-            atomicAdd((unsigned long long*)&counters[0], (unsigned long long)-1ll);  // lost the race: hand the ticket back
+            if (group_limit >= 0) atomicAdd((unsigned long long*)&counters[0], (unsigned long long)-1ll);  // lost the race
             if (prev == key) return s;
         }
         s = (s + 1) & mask;
@@ -188,20 +193,20 @@ __global__ void __launch_bounds__(256) groupby_consume_i64_sumcount_kernel(
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             if (r >= m) break;
-            uint64_t slot;
+            uint64_t sl;
             if (k[r] == EMPTY_KEY) {
-                slot = cap + 1;
+                sl = cap + 1;
                 counters[4] = 1;
             } else {
-                slot = find_or_insert(tkeys, cap, k[r], counters, group_limit);
-                if (slot == ~0ull) {
+                sl = find_or_insert(tkeys, cap, k[r], counters, group_limit);
+                if (sl == ~0ull) {
                     unsigned long long f = atomicAdd((unsigned long long*)&counters[1], 1ull);
                     fail_list[f] = (uint32_t)(i + r);
                     continue;
                 }
             }
-            if (HAS_SUM) atomicAdd(acc_sum + slot, (unsigned long long)v[r]);
-            if (HAS_CNT) atomicAdd(acc_cnt + slot, 1ull);
+            if (HAS_SUM) atomicAdd(acc_sum + sl, (unsigned long long)v[r]);
+            if (HAS_CNT) atomicAdd(acc_cnt + sl, 1ull);
         }
     }
 }
@@ -230,13 +235,7 @@ __global__ void rehash_kernel(const __grid_constant__ RehashArgs a) {
         } else {
             long long k = a.old_keys[s];
             if (k == EMPTY_KEY) continue;
-            uint64_t mask = a.new_cap - 1;
-            ns = (key_hash(k) >> 32) & mask;
-            while (true) {
-                long long prev = atomicCAS((unsigned long long*)(a.new_keys + ns), (unsigned long long)EMPTY_KEY, (unsigned long long)k);
-                if (prev == EMPTY_KEY) break;
-                ns = (ns + 1) & mask;
-            }
+            ns = find_or_insert(a.new_keys, a.new_cap, k, nullptr, -1);
         }
         for (int j = 0; j < a.n_acc; j++) a.new_acc[j][ns] = a.old_acc[j][s];
     }
@@ -369,17 +368,24 @@ struct PackArgs {
 __global__ void pack_partials_kernel(const __grid_constant__ PackArgs a) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     uint32_t na_hash = (uint32_t)xxh3_64_short(1ull, 8, SEED_HASH_PARTITION);  // hash_na_val (_array_hash.cpp:22-29)
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < a.n_out; p += stride) {
-        uint64_t s = a.slot_of_out[p];
+    int lane = threadIdx.x & 31;
+    int64_t n_round = (a.n_out + 31) & ~31ll;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_round; p += stride) {
+        bool in = p < a.n_out;
+        uint64_t s = in ? a.slot_of_out[p] : 0;
         long long key = s < a.cap ? a.tkeys[s] : (s == a.cap ? 0 : EMPTY_KEY);
         bool kvalid = s != a.cap;
         uint32_t h = kvalid ? (uint32_t)key_hash(key) : na_hash;
-        int d = hash_to_rank_u32(h, a.n_pes);
-        if (a.pass == 0) {
-            atomicAdd((unsigned long long*)&a.dest_count[d], 1ull);
-        } else {
-            long long pos = (long long)atomicAdd((unsigned long long*)&a.dest_count[d], 1ull);
-            unsigned long long* o = a.out + pos * a.row_words;
+        int d = in ? hash_to_rank_u32(h, a.n_pes) : -1;
+        // warp-aggregated cursor: one atomic per (warp, destination) instead of one per row
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        int rank_in_peers = __popc(peers & ((1u << lane) - 1));
+        long long base = 0;
+        if (in && lane == leader) base = (long long)atomicAdd((unsigned long long*)&a.dest_count[d], (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (in && a.pass == 1) {
+            unsigned long long* o = a.out + (base + rank_in_peers) * a.row_words;
             o[0] = (unsigned long long)key;
             o[1] = kvalid ? 1ull : 0ull;
             for (int j = 0; j < a.n_acc; j++) o[2 + j] = a.acc[j][s];

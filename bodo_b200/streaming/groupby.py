@@ -105,32 +105,54 @@ class GroupbyState:
 
     def _exchange(self):
         """Hash-partition exchange of the partial aggregates (one all-to-all-v), then combine."""
+        import os
+        import time
+
         import torch
         import torch.distributed as dist
+
+        trace = os.environ.get("B200_TRACE") and self.rank == 0
+        t = [time.perf_counter()]
+
+        def mark():
+            if trace:
+                torch.cuda.synchronize()
+                t.append(time.perf_counter())
 
         L = _lib.lib()
         h = self.handle
         counts = ffi.new("int64_t[]", self.n_pes)
         row_bytes = _lib.check(L.b200_groupby_shuffle_prepare(h, counts), "groupby shuffle prepare")
+        mark()
         send_counts = [int(counts[i]) for i in range(self.n_pes)]
         dev = torch.device("cuda", self.device)
         words = row_bytes // 8
-        send = torch.empty((max(sum(send_counts), 1), words), dtype=torch.int64, device=dev)
+        n_send = sum(send_counts)
+        send = torch.empty((max(n_send, 1), words), dtype=torch.int64, device=dev)
         _lib.check(L.b200_groupby_shuffle_pack(h, ffi.cast("void*", send.data_ptr())), "groupby shuffle pack")
+        mark()
+        # counts travel as one small all-gather of the n_pes x n_pes matrix (mpi_comm_info's MPI_Alltoall,
+        # _shuffle.cpp:210-213); b200_groupby_shuffle_pack returned with its stream drained, so `send` is complete
         sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
-        rc = torch.empty_like(sc)
-        dist.all_to_all_single(rc, sc, group=self.process_group)  # mpi_comm_info's MPI_Alltoall (_shuffle.cpp:210-213)
-        recv_counts = [int(x) for x in rc.cpu().tolist()]
-        recv = torch.empty((max(sum(recv_counts), 1), words), dtype=torch.int64, device=dev)
-        # b200_groupby_shuffle_pack returns with its stream drained, so `send` is complete here
-        dist.all_to_all_single(recv[: sum(recv_counts)], send[: sum(send_counts)], output_split_sizes=recv_counts,
+        allc = torch.empty(self.n_pes * self.n_pes, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, sc, group=self.process_group)
+        recv_counts = allc.view(self.n_pes, self.n_pes)[:, self.rank].tolist()
+        mark()
+        n_recv = sum(recv_counts)
+        recv = torch.empty((max(n_recv, 1), words), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv[:n_recv], send[:n_send], output_split_sizes=recv_counts,
                                input_split_sizes=send_counts, group=self.process_group)
         torch.cuda.current_stream(dev).synchronize()
-        _lib.check(L.b200_groupby_shuffle_combine(h, ffi.cast("void*", recv.data_ptr()), sum(recv_counts)),
+        mark()
+        _lib.check(L.b200_groupby_shuffle_combine(h, ffi.cast("void*", recv.data_ptr()), n_recv),
                    "groupby shuffle combine")
         L.b200_stream_synchronize(ffi.cast("void*", self.stream))
+        mark()
         self.exchanged = True
-        self.shuffle_bytes = sum(send_counts) * row_bytes
+        self.shuffle_bytes = n_send * row_bytes
+        if trace:
+            names = ["prepare", "pack", "counts", "alltoall", "combine"]
+            print("[b200 exchange ms] " + " ".join(f"{n}={(b - a) * 1e3:.3f}" for n, a, b in zip(names, t, t[1:])), flush=True)
 
 
 def _current_device() -> int:
