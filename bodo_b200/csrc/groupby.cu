@@ -11,6 +11,7 @@
 //     _groupby.cpp:3309-3341, without the partition split);
 //   * finalize compacts occupied slots and evaluates the output columns (mean_eval etc.).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -449,6 +450,245 @@ __global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
 }
 
 // ================================================================================================
+// SM-partitioned groupby (SPG): the fast path for cardinalities whose accumulators fit the chip's
+// aggregate shared memory (≈148 x 9.7k groups).  Motivation (profiles/r01_ubench*.txt): two global `red`s per
+// row cap the direct kernel at ≈85 Grows/s and the key probe halves that again, while 32-bit shared-memory
+// atomics sustain the full HBM stream rate.  So rows travel to the SM that owns their key:
+//
+//   persistent cooperative kernel, one 1024-thread CTA per SM, chunk c = one TILE-row tile per CTA:
+//     P(c): load the tile (128-bit coalesced loads), owner = mulhi(hash_hi32, n_ctas), counting-sort the
+//           tile by owner in shared memory, reserve a run in every owner's inbox (one global atomic per
+//           (CTA, owner)), copy the runs out with coalesced 16-byte stores (inboxes are L2 resident),
+//           then arrive on the chunk's global barrier counter;
+//     C(c): after all CTAs arrived for chunk c, stream the own inbox and upsert into the CTA's shared-memory
+//           hash table: key CAS (64-bit), SUM as two 32-bit native atomics with carry, COUNT as one.
+//   P(c+1) is issued before waiting for chunk c, so the barrier latency hides behind useful work; with 4 inbox
+//   buffers a CTA can never overwrite a buffer somebody still reads (see DESIGN.md §3 "SPG protocol").
+//   At the end every CTA flushes its table into the state's global table with the ordinary find-or-insert +
+//   `red` (each key has exactly one owner, so that is ≤ n_groups operations per launch).
+// Rows that do not fit (inbox run overflow, shared table full, marker key) take the direct global path in the
+// same kernel; rows that cannot even be inserted there (global table at its limit) are appended to a retry
+// list in the partial-aggregate wire format and replayed by combine_partials_kernel after the table grew.
+constexpr int SPG_THREADS = 1024;
+constexpr int SPG_NBUF = 4;
+constexpr int SPG_MAX_CTAS = 256;
+
+struct SpgArgs {
+    const long long* keys;
+    const long long* vals;
+    int64_t n_rows;
+    // global table (state)
+    long long* tkeys;
+    uint64_t cap;
+    unsigned long long* acc_sum;
+    unsigned long long* acc_cnt;
+    long long* counters;  // [0] groups, [1] retry rows, [4] marker key present, [5] error flag
+    long long group_limit;
+    // exchange buffers
+    longlong2* inbox;         // [NBUF][n_ctas][cap_rows]
+    unsigned int* inbox_cnt;  // [NBUF][n_ctas]
+    unsigned int* bar;        // [n_chunks]
+    int cap_rows;
+    int64_t n_chunks;
+    unsigned long long* retry;  // partial-aggregate rows [key][1][a0 of func 0][a0 of func 1]
+    int sum_first;              // order of the two accumulators in the wire format
+    int ns;                     // shared-memory table slots
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool HAS_SUM, bool HAS_CNT>
+__device__ __forceinline__ void spg_direct_apply(const SpgArgs& a, long long key, long long val) {
+    uint64_t sl;
+    if (key == EMPTY_KEY) { sl = a.cap + 1; a.counters[4] = 1; }
+    else {
+        sl = find_or_insert(a.tkeys, a.cap, key, a.counters, a.group_limit);
+        if (sl == ~0ull) {
+            unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
+            unsigned long long* r = a.retry + f * 4;
+            r[0] = (unsigned long long)key; r[1] = 1ull;
+            if (HAS_SUM && HAS_CNT) { r[2] = a.sum_first ? (unsigned long long)val : 1ull; r[3] = a.sum_first ? 1ull : (unsigned long long)val; }
+            else { r[2] = HAS_SUM ? (unsigned long long)val : 1ull; r[3] = 0; }
+            return;
+        }
+    }
+    if (HAS_SUM) atomicAdd(a.acc_sum + sl, (unsigned long long)val);
+    if (HAS_CNT) atomicAdd(a.acc_cnt + sl, 1ull);
+}
+
+template <bool HAS_SUM, bool HAS_CNT, int TILE>
+__global__ void __launch_bounds__(SPG_THREADS, 1) groupby_spg_kernel(const __grid_constant__ SpgArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int G = gridDim.x, me = blockIdx.x, tid = threadIdx.x;
+    const int NS = a.ns;
+    // shared layout
+    long long* skeys = (long long*)smem_raw;                              // NS x 8
+    longlong2* stage = (longlong2*)(skeys + NS);                          // TILE x 16 (NS is even -> 16B aligned)
+    unsigned int* slo = (unsigned int*)(stage + TILE);                    // NS x 4
+    unsigned int* shi = slo + NS;                                         // NS x 4
+    unsigned int* scnt = shi + NS;                                        // NS x 4
+    unsigned int* hist = scnt + NS;                                       // SPG_MAX_CTAS
+    unsigned int* lbase = hist + SPG_MAX_CTAS;                            // SPG_MAX_CTAS + 1
+    unsigned int* gbase = lbase + SPG_MAX_CTAS + 1;                       // SPG_MAX_CTAS
+    unsigned int* misc = gbase + SPG_MAX_CTAS;                            // [0] occupied slots, [1] abort flag
+    unsigned char* stage_owner = (unsigned char*)(misc + 4);              // TILE x 1
+
+    for (int s = tid; s < NS; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0; shi[s] = 0; scnt[s] = 0; }
+    if (tid < 4) misc[tid] = 0;
+    __syncthreads();
+    const unsigned int occ_limit = (unsigned int)(NS - NS / 8);  // keep 1/8 of the slots free so probing stays short
+
+    auto upsert = [&](long long key, long long val) {
+        uint64_t h = key_hash(key);
+        unsigned int s = __umulhi((unsigned int)h, (unsigned int)NS);
+        bool done = false;
+        for (int probes = 0; probes < 128; probes++) {
+            long long k = skeys[s];
+            if (k == EMPTY_KEY) {
+                unsigned int t = atomicAdd(&misc[0], 1u);
+                if (t >= occ_limit) { atomicSub(&misc[0], 1u); break; }
+                long long prev = (long long)atomicCAS((unsigned long long*)&skeys[s], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                if (prev == EMPTY_KEY) { done = true; break; }
+                atomicSub(&misc[0], 1u);
+                k = prev;
+            }
+            if (k == key) { done = true; break; }
+            s = s + 1 == (unsigned int)NS ? 0u : s + 1;
+        }
+        if (!done) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, val); return; }
+        if (HAS_SUM) {
+            unsigned int lo = (unsigned int)(unsigned long long)val, hi = (unsigned int)((unsigned long long)val >> 32);
+            unsigned int old = atomicAdd(&slo[s], lo);
+            hi += (old + lo < old) ? 1u : 0u;  // carry of this very addition
+            if (hi) atomicAdd(&shi[s], hi);
+        }
+        if (HAS_CNT) atomicAdd(&scnt[s], 1u);
+    };
+
+    auto produce = [&](int64_t c) {
+        const int buf = (int)(c % SPG_NBUF);
+        const int64_t r0 = (c * G + me) * (int64_t)TILE;
+        for (int j = tid; j < G; j += SPG_THREADS) hist[j] = 0;
+        __syncthreads();
+        constexpr int PAIRS = TILE / (2 * SPG_THREADS);
+        long long k[2 * PAIRS], v[2 * PAIRS];
+        int o[2 * PAIRS];
+        unsigned int rk[2 * PAIRS];
+#pragma unroll
+        for (int j = 0; j < PAIRS; j++) {
+            int64_t i = r0 + ((int64_t)j * SPG_THREADS + tid) * 2;
+            if (i + 1 < a.n_rows) {
+                longlong2 kk = __ldcs(reinterpret_cast<const longlong2*>(a.keys + i));
+                k[2 * j] = kk.x; k[2 * j + 1] = kk.y;
+                if (HAS_SUM) { longlong2 vv = __ldcs(reinterpret_cast<const longlong2*>(a.vals + i)); v[2 * j] = vv.x; v[2 * j + 1] = vv.y; }
+                else { v[2 * j] = 0; v[2 * j + 1] = 0; }
+                o[2 * j] = 0; o[2 * j + 1] = 0;
+            } else if (i < a.n_rows) {
+                k[2 * j] = a.keys[i]; v[2 * j] = HAS_SUM ? a.vals[i] : 0; o[2 * j] = 0;
+                k[2 * j + 1] = 0; v[2 * j + 1] = 0; o[2 * j + 1] = -1;
+            } else { k[2 * j] = k[2 * j + 1] = 0; v[2 * j] = v[2 * j + 1] = 0; o[2 * j] = o[2 * j + 1] = -1; }
+        }
+#pragma unroll
+        for (int r = 0; r < 2 * PAIRS; r++) {
+            if (o[r] < 0) continue;
+            if (k[r] == EMPTY_KEY) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, k[r], v[r]); o[r] = -1; continue; }
+            o[r] = (int)__umulhi((unsigned int)(key_hash(k[r]) >> 32), (unsigned int)G);
+            rk[r] = atomicAdd(&hist[o[r]], 1u);
+        }
+        __syncthreads();
+        // reserve a run in every owner's inbox; exclusive scan of the histogram by warp 0
+        if (tid < G) { unsigned int cnt = hist[tid]; gbase[tid] = cnt ? atomicAdd(&a.inbox_cnt[buf * G + tid], cnt) : 0u; }
+        if (tid < 32) {
+            unsigned int carry = 0;
+            for (int base = 0; base < G; base += 32) {
+                int j = base + tid;
+                unsigned int x = j < G ? hist[j] : 0u, inc = x;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { unsigned int y = __shfl_up_sync(0xffffffffu, inc, d); if (tid >= d) inc += y; }
+                if (j < G) lbase[j] = carry + inc - x;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (tid == 0) lbase[G] = carry;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 2 * PAIRS; r++) {
+            if (o[r] < 0) continue;
+            unsigned int p = lbase[o[r]] + rk[r];
+            stage[p] = make_longlong2(k[r], v[r]);
+            stage_owner[p] = (unsigned char)o[r];
+        }
+        __syncthreads();
+        const unsigned int n_tile = lbase[G];
+        for (unsigned int p = tid; p < n_tile; p += SPG_THREADS) {
+            unsigned int ow = stage_owner[p];
+            unsigned int off = gbase[ow] + (p - lbase[ow]);
+            longlong2 row = stage[p];
+            if (off < (unsigned int)a.cap_rows) a.inbox[((size_t)buf * G + ow) * a.cap_rows + off] = row;
+            else spg_direct_apply<HAS_SUM, HAS_CNT>(a, row.x, row.y);  // run does not fit: direct path
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicAdd(&a.bar[c], 1u); }
+    };
+
+    auto wait_chunk = [&](int64_t c) -> bool {
+        if (tid == 0) {
+            unsigned long long spins = 0;
+            while (ld_acquire_u32(&a.bar[c]) < (unsigned int)G) {
+                if (++spins > (1ull << 24)) { misc[1] = 1; a.counters[5] = 1; break; }  // never hang the GPU
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        return misc[1] == 0;
+    };
+
+    auto consume = [&](int64_t c) {
+        const int buf = (int)(c % SPG_NBUF);
+        unsigned int n_in = __ldcg(&a.inbox_cnt[buf * G + me]);
+        if (n_in > (unsigned int)a.cap_rows) n_in = (unsigned int)a.cap_rows;
+        const longlong2* src = a.inbox + ((size_t)buf * G + me) * a.cap_rows;
+        for (unsigned int p = tid; p < n_in; p += SPG_THREADS) {
+            longlong2 row = __ldcg(src + p);
+            upsert(row.x, row.y);
+        }
+        __syncthreads();
+        if (tid == 0) a.inbox_cnt[buf * G + me] = 0;  // ordered before this CTA's next arrive (fence + atomic)
+    };
+
+    bool ok = true;
+    if (a.n_chunks > 0) produce(0);
+    for (int64_t c = 0; c < a.n_chunks && ok; c++) {
+        if (c + 1 < a.n_chunks) produce(c + 1);
+        ok = wait_chunk(c);
+        if (ok) consume(c);
+    }
+    __syncthreads();
+    // flush the shared table into the state's global table
+    for (int s = tid; s < NS; s += SPG_THREADS) {
+        long long key = skeys[s];
+        if (key == EMPTY_KEY) continue;
+        unsigned long long sum = (unsigned long long)slo[s] | ((unsigned long long)shi[s] << 32);
+        unsigned long long cnt = scnt[s];
+        uint64_t sl = find_or_insert(a.tkeys, a.cap, key, a.counters, a.group_limit);
+        if (sl == ~0ull) {
+            unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
+            unsigned long long* r = a.retry + f * 4;
+            r[0] = (unsigned long long)key; r[1] = 1ull;
+            if (HAS_SUM && HAS_CNT) { r[2] = a.sum_first ? sum : cnt; r[3] = a.sum_first ? cnt : sum; }
+            else { r[2] = HAS_SUM ? sum : cnt; r[3] = 0; }
+            continue;
+        }
+        if (HAS_SUM) atomicAdd(a.acc_sum + sl, sum);
+        if (HAS_CNT) atomicAdd(a.acc_cnt + sl, cnt);
+    }
+}
+
+// ================================================================================================
 // Host side
 // ================================================================================================
 
@@ -577,6 +817,7 @@ class GroupbyState {
         d_counters.alloc(8 * sizeof(long long));
         B200_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(long long), stream));
         B200_CUDA(cudaMallocHost((void**)&h_counters, 8 * sizeof(long long)));
+        expected_groups_hint = expected_groups > 0 ? expected_groups : 0;
         uint64_t want = 1ull << 16;
         if (expected_groups > 0) { while (want < (uint64_t)expected_groups * 2) want <<= 1; }
         else want = 1ull << 21;
@@ -666,11 +907,112 @@ class GroupbyState {
         (void)chunk_rows;
     }
 
+    // ---- SM-partitioned fast path (SPG) ----
+    static constexpr int SPG_TILE = 2048;
+    static constexpr int64_t SPG_LAUNCH_ROWS = 1ll << 26;
+    DevBuf d_inbox, d_inbox_cnt, d_bar, d_retry;
+    int spg_ctas = 0, spg_ns = 0, spg_cap_rows = 0;
+    size_t spg_smem = 0;
+    int spg_state = -1;  // -1 not probed, 0 unavailable/disabled, 1 ready
+    int64_t spg_launches = 0, spg_retry_rows = 0;
+    int64_t expected_groups_hint = 0;
+
+    template <bool S, bool C>
+    static const void* spg_func() { return (const void*)groupby_spg_kernel<S, C, SPG_TILE>; }
+
+    bool spg_probe() {
+        if (spg_state >= 0) return spg_state == 1;
+        spg_state = 0;
+        const char* env = getenv("B200_SPG");
+        if (env && env[0] == '0') return false;
+        int coop = 0, max_smem = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (!coop || sms > SPG_MAX_CTAS - 1) return false;
+        size_t fixed = (size_t)SPG_TILE * 17 + (3 * SPG_MAX_CTAS + 1 + 4) * 4 + 64;
+        if ((size_t)max_smem < fixed + 20 * 1024) return false;
+        spg_ns = (int)(((size_t)max_smem - fixed) / 20) & ~1;
+        spg_smem = (size_t)spg_ns * 20 + fixed;
+        const void* fns[3] = {spg_func<true, true>(), spg_func<true, false>(), spg_func<false, true>()};
+        for (auto f : fns) {
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_smem) != cudaSuccess) { cudaGetLastError(); return false; }
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, SPG_THREADS, spg_smem) != cudaSuccess || nb < 1) { cudaGetLastError(); return false; }
+        }
+        spg_ctas = sms;
+        // rows per owner per chunk: mean TILE, sd sqrt(TILE) for uniform keys; leave 25 % head room
+        spg_cap_rows = (SPG_TILE + SPG_TILE / 4 + 63) & ~63;
+        d_inbox.alloc((size_t)SPG_NBUF * spg_ctas * spg_cap_rows * 16);
+        d_inbox_cnt.alloc((size_t)SPG_NBUF * spg_ctas * 4);
+        spg_state = 1;
+        return true;
+    }
+
+    // groups the shared-memory tables of all CTAs can hold together (7/8 of the slots, see occ_limit)
+    int64_t spg_group_capacity() const { return (int64_t)spg_ctas * (spg_ns - spg_ns / 8); }
+
+    void consume_spg(const long long* keys, const long long* vals, int64_t n, int sum_j, int cnt_j) {
+        for (int64_t r0 = 0; r0 < n; r0 += SPG_LAUNCH_ROWS) {
+            int64_t rows = std::min(SPG_LAUNCH_ROWS, n - r0);
+            // the flush inserts at most ctas * ns groups; keep that much room so the common case never retries
+            while ((int64_t)(cap / 2) < n_groups_bound + (int64_t)spg_ctas * spg_ns + 1024) grow(cap * 2);
+            int64_t per_chunk = (int64_t)spg_ctas * SPG_TILE;
+            int64_t n_chunks = (rows + per_chunk - 1) / per_chunk;
+            d_bar.ensure((size_t)n_chunks * 4);
+            d_retry.ensure(((size_t)rows + (size_t)spg_ctas * spg_ns) * 32);
+            B200_CUDA(cudaMemsetAsync(d_bar.p, 0, (size_t)n_chunks * 4, stream));
+            B200_CUDA(cudaMemsetAsync(d_inbox_cnt.p, 0, (size_t)SPG_NBUF * spg_ctas * 4, stream));
+            B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8, 0, 8, stream));       // retry rows
+            B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 5 * 8, 0, 8, stream));   // error flag
+            SpgArgs a{};
+            a.keys = keys + r0; a.vals = vals ? vals + r0 : nullptr; a.n_rows = rows;
+            a.tkeys = d_keys.as<long long>(); a.cap = cap;
+            a.acc_sum = sum_j >= 0 ? d_a0[sum_j].as<unsigned long long>() : nullptr;
+            a.acc_cnt = cnt_j >= 0 ? d_a0[cnt_j].as<unsigned long long>() : nullptr;
+            a.counters = d_counters.as<long long>(); a.group_limit = (long long)(cap / 2);
+            a.inbox = d_inbox.as<longlong2>(); a.inbox_cnt = d_inbox_cnt.as<unsigned int>(); a.bar = d_bar.as<unsigned int>();
+            a.cap_rows = spg_cap_rows; a.n_chunks = n_chunks; a.retry = d_retry.as<unsigned long long>();
+            a.sum_first = (sum_j >= 0 && cnt_j >= 0 && sum_j < cnt_j) ? 1 : 0; a.ns = spg_ns;
+            const void* f = (sum_j >= 0 && cnt_j >= 0) ? spg_func<true, true>() : (sum_j >= 0 ? spg_func<true, false>() : spg_func<false, true>());
+            void* params[1] = {(void*)&a};
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (profiling) { B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1)); B200_CUDA(cudaEventRecord(ev0, stream)); }
+            B200_CUDA(cudaLaunchCooperativeKernel(f, dim3(spg_ctas), dim3(SPG_THREADS), params, spg_smem, stream));
+            if (ev0) { B200_CUDA(cudaEventRecord(ev1, stream)); prof_events.emplace_back(ev0, ev1); }
+            launches++; consume_launches++; spg_launches++;
+            read_counters();
+            if (h_counters[5]) throw Error("b200 groupby: SPG kernel aborted (inter-CTA barrier timed out); set B200_SPG=0 to use the direct kernel");
+            // rows / partials that found the global table full: grow, then merge them like received partial rows
+            while (h_counters[1] > 0) {
+                int64_t nr = h_counters[1];
+                spg_retry_rows += nr;
+                uint64_t nc = cap;
+                while (nc < 2ull * (uint64_t)(n_groups + nr)) nc <<= 1;
+                if (nc == cap) nc <<= 1;
+                grow(nc);
+                B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8, 0, 8, stream));
+                CombineArgs c{};
+                c.in = d_retry.as<unsigned long long>(); c.n_rows = nr; c.row_words = 4;
+                c.tkeys = d_keys.as<long long>(); c.cap = cap; c.counters = d_counters.as<long long>(); c.group_limit = (long long)(cap / 2);
+                c.fail_list = nullptr; c.index_list = nullptr; c.n_ops = 0;
+                // wire order = function order of the (at most two) accumulators
+                int order[2] = {sum_j, cnt_j};
+                if (sum_j >= 0 && cnt_j >= 0 && cnt_j < sum_j) std::swap(order[0], order[1]);
+                if (order[0] < 0) std::swap(order[0], order[1]);
+                for (int q = 0; q < 2; q++) if (order[q] >= 0) { c.kinds[c.n_ops] = K_SUM_I64; c.a0[c.n_ops] = d_a0[order[q]].p; c.a1[c.n_ops] = nullptr; c.n_ops++; }
+                combine_partials_kernel<<<grid_for(nr), 256, 0, stream>>>(c);
+                launches++;
+                B200_CUDA(cudaGetLastError());
+                read_counters();
+            }
+            n_groups_bound = n_groups;
+            rows_consumed += rows;
+        }
+    }
+
     // Consume rows [0, n) of device-resident columns.
     void consume_device_chunk(const std::vector<const void*>& data, const std::vector<const uint8_t*>& valid, int64_t n) {
         if (n == 0) return;
-        bool could_fail = (int64_t)(cap / 2) - n_groups_bound < n;
-        if (could_fail) d_fail.ensure((size_t)n * 4);
         // fast path: non-null int64 key + {sum, count/size} over one non-null int64 value column
         bool fast = c_types[0] == CT_INT64 && valid[0] == nullptr && n_funcs >= 1;
         int sum_j = -1, cnt_j = -1, vcol = -1;
@@ -685,6 +1027,35 @@ class GroupbyState {
             }
         }
         if (fast && (((uintptr_t)data[0] & 15) || (vcol >= 0 && ((uintptr_t)data[vcol] & 15)))) fast = false;
+        // SM-partitioned path: big batches whose (estimated) cardinality fits the chip's shared memory
+        if (fast && n >= (1 << 20) && spg_probe()) {
+            const char* env = getenv("B200_SPG");
+            bool force = env && env[0] == '1';
+            int64_t est = std::max(expected_groups_hint, n_groups);
+            if (!force && est == 0 && rows_consumed == 0) {
+                // cardinality unknown: learn it from a prefix through the direct kernel
+                int64_t prefix = std::min<int64_t>(n, 1 << 20);
+                std::vector<const void*> d2(data); std::vector<const uint8_t*> v2(valid);
+                consume_direct(d2, v2, prefix, fast, sum_j, cnt_j, vcol, /*force_count=*/true);
+                est = n_groups;
+                if (prefix == n) return;
+                for (int c = 0; c < n_cols; c++) if (data[c]) d2[c] = (const char*)data[c] + prefix * ctype_size(c_types[c]);
+                if (est <= spg_group_capacity()) consume_spg((const long long*)d2[0], vcol >= 0 ? (const long long*)d2[vcol] : nullptr, n - prefix, sum_j, cnt_j);
+                else consume_direct(d2, v2, n - prefix, fast, sum_j, cnt_j, vcol, false);
+                return;
+            }
+            if (force || est <= spg_group_capacity()) {
+                consume_spg((const long long*)data[0], vcol >= 0 ? (const long long*)data[vcol] : nullptr, n, sum_j, cnt_j);
+                return;
+            }
+        }
+        consume_direct(data, valid, n, fast, sum_j, cnt_j, vcol, false);
+    }
+
+    void consume_direct(const std::vector<const void*>& data, const std::vector<const uint8_t*>& valid, int64_t n, bool fast, int sum_j,
+                        int cnt_j, int vcol, bool force_count) {
+        bool could_fail = force_count || (int64_t)(cap / 2) - n_groups_bound < n;
+        if (could_fail) d_fail.ensure((size_t)n * 4);
         // table pointers are looked up at launch time: grow() replaces them between a launch and its replay
         auto launch = [&](const uint32_t* index_list, int64_t rows) {
             long long* ctr = d_counters.as<long long>();
@@ -1030,6 +1401,8 @@ int64_t b200_groupby_get_metric(void* state, int32_t which) {
         case 5: return s->fail_rows;
         case 6: return (int64_t)s->consume_kernel_us();
         case 7: return s->consume_launches;
+        case 8: return s->spg_launches;
+        case 9: return s->spg_retry_rows;
         case 100: s->profiling = true; return 0;
         default: return -1;
     }

@@ -136,3 +136,32 @@ def test_unsupported_function_fails_loudly(gpu_lib):
     from bodo_b200.streaming.groupby import init_groupby_state
     with pytest.raises(B200Error, match="unsupported aggregate function"):
         init_groupby_state(-1, (0,), ("median",), (0, 1), (1,))
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("n_groups,hint", [(1000, 0), (50_000, 50_000), (1_000_000, 1_000_000), (3_000_000, 16)])
+@pytest.mark.parametrize("funcs", [("sum", "count"), ("count", "sum"), ("sum",), ("size",)])
+def test_sm_partitioned_path_vs_oracle(gpu_lib, oracle, n_groups, hint, funcs):
+    # >= 1 Mi-row device batches of the headline shape take the SM-partitioned kernel (when its estimate of the
+    # cardinality fits shared memory); 3 M groups with a tiny hint overflows the shared tables and the global table,
+    # exercising the in-kernel direct path and the retry list.  Result must be bit-exact either way.
+    from bodo_b200.streaming.groupby import get_metric
+    n = 2_600_001
+    k, v = oracle.synth_fill(0, n, n_groups, 13)
+    t = Table.from_pandas(pd.DataFrame({"k": k, "v": v}))
+    nf = len(funcs)
+    from bodo_b200.streaming.groupby import (delete_groupby_state, groupby_build_consume_batch,
+                                             groupby_produce_output_batch, init_groupby_state)
+    from tests.helpers import table_to_device
+    st = init_groupby_state(-1, (0,), funcs, tuple(range(nf + 1)) if "size" not in funcs else (0, 0), (1,) * (0 if funcs == ("size",) else nf),
+                            expected_groups=hint, output_batch_size=1 << 30)
+    dt = table_to_device(t)
+    groupby_build_consume_batch(st, dt, True, True)
+    used_spg = get_metric(st, 8)
+    out, last = groupby_produce_output_batch(st, True)
+    got = out.to_pandas()
+    delete_groupby_state(st)
+    exp = oracle_groupby_frame(oracle, t, 0, list(funcs), [None if f == "size" else 1 for f in funcs])
+    assert_frames_equal(positional(got), exp)
+    if n_groups <= 1_000_000:
+        assert used_spg >= 1, "the SM-partitioned kernel was expected to run for this shape"
