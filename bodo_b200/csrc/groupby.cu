@@ -451,140 +451,102 @@ __global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
 
 // ================================================================================================
 // SM-partitioned groupby (SPG): the fast path for cardinalities whose accumulators fit the chip's
-// aggregate shared memory (≈148 x 9.7k groups).  Motivation (profiles/r01_ubench*.txt): two global `red`s per
-// row cap the direct kernel at ≈85 Grows/s and the key probe halves that again, while 32-bit shared-memory
-// atomics sustain the full HBM stream rate.  So rows travel to the SM that owns their key:
+// aggregate shared memory (≈148 x 10k groups).  Motivation (profiles/r01_ubench*.txt): two global `red`s per
+// row cap the direct kernel at ≈85 Grows/s and the key probe halves that again (L2 random-request rate), while
+// 32-bit shared-memory atomics sustain the full HBM stream rate.  So rows travel to the SM that owns their key:
 //
-//   persistent cooperative kernel, one 1024-thread CTA per SM, chunk c = one TILE-row tile per CTA:
-//     P(c): load the tile (128-bit coalesced loads), owner = mulhi(hash_hi32, n_ctas), counting-sort the
-//           tile by owner in shared memory, reserve a run in every owner's inbox (one global atomic per
-//           (CTA, owner)), copy the runs out with coalesced 16-byte stores (inboxes are L2 resident),
-//           then arrive on the chunk's global barrier counter;
-//     C(c): after all CTAs arrived for chunk c, stream the own inbox and upsert into the CTA's shared-memory
-//           hash table: key CAS (64-bit), SUM as two 32-bit native atomics with carry, COUNT as one.
-//   P(c+1) is issued before waiting for chunk c, so the barrier latency hides behind useful work; with 4 inbox
-//   buffers a CTA can never overwrite a buffer somebody still reads (see DESIGN.md §3 "SPG protocol").
-//   At the end every CTA flushes its table into the state's global table with the ordinary find-or-insert +
-//   `red` (each key has exactly one owner, so that is ≤ n_groups operations per launch).
-// Rows that do not fit (inbox run overflow, shared table full, marker key) take the direct global path in the
-// same kernel; rows that cannot even be inserted there (global table at its limit) are appended to a retry
-// list in the partial-aggregate wire format and replayed by combine_partials_kernel after the table grew.
-constexpr int SPG_THREADS = 1024;
-constexpr int SPG_NBUF = 4;
-constexpr int SPG_MAX_CTAS = 256;
+//   K1 spg_partition_kernel : every CTA counting-sorts TILE-row tiles by owner (= mulhi(hash, n_owners)) in
+//        shared memory, reserves one run per owner with a single global atomic per (tile, owner) and copies
+//        the runs out with coalesced 16-byte stores -> owner buckets of (key, value) rows in HBM.
+//   K2 spg_aggregate_kernel : one CTA per owner streams its bucket into a shared-memory hash table (key CAS,
+//        SUM = two native 32-bit atomics with carry, COUNT = one), then flushes the table into the state's
+//        global table with the ordinary find-or-insert + `red` (each key has one owner: <= n_groups per launch).
+//   Algorithmic HBM traffic: 16 B/row read + 16 B/row bucket write + 16 B/row bucket read.
+// A persistent single-kernel variant (L2-resident inboxes, inter-CTA barriers) was measured slower
+// (profiles/r01_spg_persistent.txt): per-chunk work per SM is too small to amortise the barrier latency.
+// Rows that do not fit (bucket overflow under skew, shared table full, marker key) take the direct global path
+// inside the same kernels; rows that cannot even be inserted there (global table at its limit) are appended to
+// a retry list in the partial-aggregate wire format and replayed by combine_partials_kernel after the table grew.
+constexpr int SPG_THREADS = 1024;   // K2 (aggregate) threads per CTA
+constexpr int SPG_PTHREADS = 512;   // K1 (partition) threads per CTA, 2 CTAs per SM
+constexpr int SPG_TILE = 4096;
+constexpr int SPG_MAX_OWNERS = 256;
 
 struct SpgArgs {
     const long long* keys;
     const long long* vals;
     int64_t n_rows;
+    int n_owners;
     // global table (state)
     long long* tkeys;
     uint64_t cap;
     unsigned long long* acc_sum;
     unsigned long long* acc_cnt;
-    long long* counters;  // [0] groups, [1] retry rows, [4] marker key present, [5] error flag
+    long long* counters;  // [0] groups, [1] retry rows, [4] marker key present
     long long group_limit;
-    // exchange buffers
-    longlong2* inbox;         // [NBUF][n_ctas][cap_rows]
-    unsigned int* inbox_cnt;  // [NBUF][n_ctas]
-    unsigned int* bar;        // [n_chunks]
-    int cap_rows;
-    int64_t n_chunks;
+    // owner buckets
+    longlong2* bucket;            // [n_owners][bucket_cap]
+    unsigned long long* bucket_cnt;  // [n_owners] rows appended (may exceed bucket_cap: the excess went the direct way)
+    long long bucket_cap;
     unsigned long long* retry;  // partial-aggregate rows [key][1][a0 of func 0][a0 of func 1]
     int sum_first;              // order of the two accumulators in the wire format
-    int ns;                     // shared-memory table slots
+    int ns;                     // shared-memory table slots (K2)
 };
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// cheap in-kernel hash for owner / shared-table slot (placement inside one GPU is free to choose; the rank
+// placement that must match the reference uses xxh3, see shuffle.cu)
+__device__ __forceinline__ uint64_t spg_hash(long long key) {
+    uint64_t x = (uint64_t)key;
+    return (x ^ (x >> 29)) * 0x9E3779B97F4A7C15ULL;
 }
+__device__ __forceinline__ unsigned int spg_owner(uint64_t h, int n_owners) { return __umulhi((unsigned int)(h >> 32), (unsigned int)n_owners); }
+__device__ __forceinline__ unsigned int spg_slot(uint64_t h, int ns) { return __umulhi((unsigned int)(h >> 20), (unsigned int)ns); }
 
 template <bool HAS_SUM, bool HAS_CNT>
-__device__ __forceinline__ void spg_direct_apply(const SpgArgs& a, long long key, long long val) {
+__device__ __forceinline__ void spg_retry_row(const SpgArgs& a, long long key, unsigned long long sum, unsigned long long cnt) {
+    unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
+    unsigned long long* r = a.retry + f * 4;
+    r[0] = (unsigned long long)key; r[1] = 1ull;
+    if (HAS_SUM && HAS_CNT) { r[2] = a.sum_first ? sum : cnt; r[3] = a.sum_first ? cnt : sum; }
+    else { r[2] = HAS_SUM ? sum : cnt; r[3] = 0; }
+}
+template <bool HAS_SUM, bool HAS_CNT>
+__device__ __forceinline__ void spg_direct_apply(const SpgArgs& a, long long key, unsigned long long sum, unsigned long long cnt) {
     uint64_t sl;
     if (key == EMPTY_KEY) { sl = a.cap + 1; a.counters[4] = 1; }
     else {
         sl = find_or_insert(a.tkeys, a.cap, key, a.counters, a.group_limit);
-        if (sl == ~0ull) {
-            unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
-            unsigned long long* r = a.retry + f * 4;
-            r[0] = (unsigned long long)key; r[1] = 1ull;
-            if (HAS_SUM && HAS_CNT) { r[2] = a.sum_first ? (unsigned long long)val : 1ull; r[3] = a.sum_first ? 1ull : (unsigned long long)val; }
-            else { r[2] = HAS_SUM ? (unsigned long long)val : 1ull; r[3] = 0; }
-            return;
-        }
+        if (sl == ~0ull) { spg_retry_row<HAS_SUM, HAS_CNT>(a, key, sum, cnt); return; }
     }
-    if (HAS_SUM) atomicAdd(a.acc_sum + sl, (unsigned long long)val);
-    if (HAS_CNT) atomicAdd(a.acc_cnt + sl, 1ull);
+    if (HAS_SUM) atomicAdd(a.acc_sum + sl, sum);
+    if (HAS_CNT) atomicAdd(a.acc_cnt + sl, cnt);
 }
 
-template <bool HAS_SUM, bool HAS_CNT, int TILE>
-__global__ void __launch_bounds__(SPG_THREADS, 1) groupby_spg_kernel(const __grid_constant__ SpgArgs a) {
+// K1: partition rows into owner buckets. grid = persistent (2 CTAs / SM), tiles are taken grid-stride.
+template <bool HAS_SUM, bool HAS_CNT>
+__global__ void __launch_bounds__(SPG_PTHREADS, 2) spg_partition_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int G = gridDim.x, me = blockIdx.x, tid = threadIdx.x;
-    const int NS = a.ns;
-    // shared layout
-    long long* skeys = (long long*)smem_raw;                              // NS x 8
-    longlong2* stage = (longlong2*)(skeys + NS);                          // TILE x 16 (NS is even -> 16B aligned)
-    unsigned int* slo = (unsigned int*)(stage + TILE);                    // NS x 4
-    unsigned int* shi = slo + NS;                                         // NS x 4
-    unsigned int* scnt = shi + NS;                                        // NS x 4
-    unsigned int* hist = scnt + NS;                                       // SPG_MAX_CTAS
-    unsigned int* lbase = hist + SPG_MAX_CTAS;                            // SPG_MAX_CTAS + 1
-    unsigned int* gbase = lbase + SPG_MAX_CTAS + 1;                       // SPG_MAX_CTAS
-    unsigned int* misc = gbase + SPG_MAX_CTAS;                            // [0] occupied slots, [1] abort flag
-    unsigned char* stage_owner = (unsigned char*)(misc + 4);              // TILE x 1
-
-    for (int s = tid; s < NS; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0; shi[s] = 0; scnt[s] = 0; }
-    if (tid < 4) misc[tid] = 0;
-    __syncthreads();
-    const unsigned int occ_limit = (unsigned int)(NS - NS / 8);  // keep 1/8 of the slots free so probing stays short
-
-    auto upsert = [&](long long key, long long val) {
-        uint64_t h = key_hash(key);
-        unsigned int s = __umulhi((unsigned int)h, (unsigned int)NS);
-        bool done = false;
-        for (int probes = 0; probes < 128; probes++) {
-            long long k = skeys[s];
-            if (k == EMPTY_KEY) {
-                unsigned int t = atomicAdd(&misc[0], 1u);
-                if (t >= occ_limit) { atomicSub(&misc[0], 1u); break; }
-                long long prev = (long long)atomicCAS((unsigned long long*)&skeys[s], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-                if (prev == EMPTY_KEY) { done = true; break; }
-                atomicSub(&misc[0], 1u);
-                k = prev;
-            }
-            if (k == key) { done = true; break; }
-            s = s + 1 == (unsigned int)NS ? 0u : s + 1;
-        }
-        if (!done) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, val); return; }
-        if (HAS_SUM) {
-            unsigned int lo = (unsigned int)(unsigned long long)val, hi = (unsigned int)((unsigned long long)val >> 32);
-            unsigned int old = atomicAdd(&slo[s], lo);
-            hi += (old + lo < old) ? 1u : 0u;  // carry of this very addition
-            if (hi) atomicAdd(&shi[s], hi);
-        }
-        if (HAS_CNT) atomicAdd(&scnt[s], 1u);
-    };
-
-    auto produce = [&](int64_t c) {
-        const int buf = (int)(c % SPG_NBUF);
-        const int64_t r0 = (c * G + me) * (int64_t)TILE;
-        for (int j = tid; j < G; j += SPG_THREADS) hist[j] = 0;
-        __syncthreads();
-        constexpr int PAIRS = TILE / (2 * SPG_THREADS);
-        long long k[2 * PAIRS], v[2 * PAIRS];
-        int o[2 * PAIRS];
-        unsigned int rk[2 * PAIRS];
+    longlong2* stage = (longlong2*)smem_raw;                                   // SPG_TILE x 16
+    unsigned long long* gbase = (unsigned long long*)(stage + SPG_TILE);      // SPG_MAX_OWNERS x 8
+    unsigned int* hist = (unsigned int*)(gbase + SPG_MAX_OWNERS);             // SPG_MAX_OWNERS
+    unsigned int* lbase = hist + SPG_MAX_OWNERS;                               // SPG_MAX_OWNERS + 1
+    unsigned char* stage_owner = (unsigned char*)(lbase + SPG_MAX_OWNERS + 4);  // SPG_TILE
+    const int G = a.n_owners, tid = threadIdx.x;
+    constexpr int ROWS = SPG_TILE / SPG_PTHREADS;  // 8 rows per thread per tile, as 4 adjacent pairs
+    constexpr int PAIRS = ROWS / 2;
+    const int64_t n_tiles = (a.n_rows + SPG_TILE - 1) / SPG_TILE;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t r0 = t * SPG_TILE;
+        long long k[ROWS], v[ROWS];
+        int o[ROWS];
+        unsigned int rk[ROWS];
 #pragma unroll
         for (int j = 0; j < PAIRS; j++) {
-            int64_t i = r0 + ((int64_t)j * SPG_THREADS + tid) * 2;
+            int64_t i = r0 + ((int64_t)j * SPG_PTHREADS + tid) * 2;
             if (i + 1 < a.n_rows) {
-                longlong2 kk = __ldcs(reinterpret_cast<const longlong2*>(a.keys + i));
-                k[2 * j] = kk.x; k[2 * j + 1] = kk.y;
-                if (HAS_SUM) { longlong2 vv = __ldcs(reinterpret_cast<const longlong2*>(a.vals + i)); v[2 * j] = vv.x; v[2 * j + 1] = vv.y; }
+                longlong2 t2 = __ldcs(reinterpret_cast<const longlong2*>(a.keys + i));
+                k[2 * j] = t2.x; k[2 * j + 1] = t2.y;
+                if (HAS_SUM) { longlong2 u2 = __ldcs(reinterpret_cast<const longlong2*>(a.vals + i)); v[2 * j] = u2.x; v[2 * j + 1] = u2.y; }
                 else { v[2 * j] = 0; v[2 * j + 1] = 0; }
                 o[2 * j] = 0; o[2 * j + 1] = 0;
             } else if (i < a.n_rows) {
@@ -592,16 +554,18 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) groupby_spg_kernel(const __gri
                 k[2 * j + 1] = 0; v[2 * j + 1] = 0; o[2 * j + 1] = -1;
             } else { k[2 * j] = k[2 * j + 1] = 0; v[2 * j] = v[2 * j + 1] = 0; o[2 * j] = o[2 * j + 1] = -1; }
         }
+        for (int j = tid; j < G; j += SPG_PTHREADS) hist[j] = 0;
+        __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 2 * PAIRS; r++) {
+        for (int r = 0; r < ROWS; r++) {
             if (o[r] < 0) continue;
-            if (k[r] == EMPTY_KEY) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, k[r], v[r]); o[r] = -1; continue; }
-            o[r] = (int)__umulhi((unsigned int)(key_hash(k[r]) >> 32), (unsigned int)G);
+            if (k[r] == EMPTY_KEY) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, k[r], (unsigned long long)v[r], 1ull); o[r] = -1; continue; }
+            o[r] = (int)spg_owner(spg_hash(k[r]), G);
             rk[r] = atomicAdd(&hist[o[r]], 1u);
         }
         __syncthreads();
-        // reserve a run in every owner's inbox; exclusive scan of the histogram by warp 0
-        if (tid < G) { unsigned int cnt = hist[tid]; gbase[tid] = cnt ? atomicAdd(&a.inbox_cnt[buf * G + tid], cnt) : 0u; }
+        // reserve one run per owner; exclusive scan of the histogram by warp 0
+        if (tid < G) { unsigned int cnt = hist[tid]; gbase[tid] = cnt ? atomicAdd(&a.bucket_cnt[tid], (unsigned long long)cnt) : 0ull; }
         if (tid < 32) {
             unsigned int carry = 0;
             for (int base = 0; base < G; base += 32) {
@@ -616,7 +580,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) groupby_spg_kernel(const __gri
         }
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 2 * PAIRS; r++) {
+        for (int r = 0; r < ROWS; r++) {
             if (o[r] < 0) continue;
             unsigned int p = lbase[o[r]] + rk[r];
             stage[p] = make_longlong2(k[r], v[r]);
@@ -624,48 +588,72 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) groupby_spg_kernel(const __gri
         }
         __syncthreads();
         const unsigned int n_tile = lbase[G];
-        for (unsigned int p = tid; p < n_tile; p += SPG_THREADS) {
+        for (unsigned int p = tid; p < n_tile; p += SPG_PTHREADS) {
             unsigned int ow = stage_owner[p];
-            unsigned int off = gbase[ow] + (p - lbase[ow]);
+            unsigned long long off = gbase[ow] + (p - lbase[ow]);
             longlong2 row = stage[p];
-            if (off < (unsigned int)a.cap_rows) a.inbox[((size_t)buf * G + ow) * a.cap_rows + off] = row;
-            else spg_direct_apply<HAS_SUM, HAS_CNT>(a, row.x, row.y);  // run does not fit: direct path
+            if (off < (unsigned long long)a.bucket_cap) a.bucket[(size_t)ow * a.bucket_cap + off] = row;
+            else spg_direct_apply<HAS_SUM, HAS_CNT>(a, row.x, (unsigned long long)row.y, 1ull);  // bucket full (skew): direct path
         }
         __syncthreads();
-        if (tid == 0) { __threadfence(); atomicAdd(&a.bar[c], 1u); }
-    };
+    }
+}
 
-    auto wait_chunk = [&](int64_t c) -> bool {
-        if (tid == 0) {
-            unsigned long long spins = 0;
-            while (ld_acquire_u32(&a.bar[c]) < (unsigned int)G) {
-                if (++spins > (1ull << 24)) { misc[1] = 1; a.counters[5] = 1; break; }  // never hang the GPU
-                __nanosleep(64);
+// K2: one CTA per owner aggregates its bucket in shared memory, then flushes into the global table.
+template <bool HAS_SUM, bool HAS_CNT>
+__global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __grid_constant__ SpgArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NS = a.ns, tid = threadIdx.x, me = blockIdx.x;
+    long long* skeys = (long long*)smem_raw;      // NS x 8
+    unsigned int* slo = (unsigned int*)(skeys + NS);  // NS x 4
+    unsigned int* shi = slo + NS;
+    unsigned int* scnt = shi + NS;
+    unsigned int* misc = scnt + NS;  // [0] occupied slots
+    for (int s = tid; s < NS; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0; shi[s] = 0; scnt[s] = 0; }
+    if (tid == 0) misc[0] = 0;
+    __syncthreads();
+    const unsigned int occ_limit = (unsigned int)(NS - NS / 8);  // keep 1/8 of the slots free so probing stays short
+
+    auto upsert = [&](long long key, long long val) {
+        unsigned int s = spg_slot(spg_hash(key), NS);
+        bool done = false;
+        for (int probes = 0; probes < 256; probes++) {
+            long long kk = skeys[s];
+            if (kk == EMPTY_KEY) {
+                unsigned int t = atomicAdd(&misc[0], 1u);
+                if (t >= occ_limit) { atomicSub(&misc[0], 1u); break; }
+                long long prev = (long long)atomicCAS((unsigned long long*)&skeys[s], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                if (prev == EMPTY_KEY) { done = true; break; }
+                atomicSub(&misc[0], 1u);
+                kk = prev;
             }
+            if (kk == key) { done = true; break; }
+            s = s + 1 == (unsigned int)NS ? 0u : s + 1;
         }
-        __syncthreads();
-        return misc[1] == 0;
+        if (!done) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, (unsigned long long)val, 1ull); return; }
+        if (HAS_SUM) {
+            unsigned int lo = (unsigned int)(unsigned long long)val, hi = (unsigned int)((unsigned long long)val >> 32);
+            unsigned int old = atomicAdd(&slo[s], lo);
+            hi += (old + lo < old) ? 1u : 0u;  // carry of this very addition
+            if (hi) atomicAdd(&shi[s], hi);
+        }
+        if (HAS_CNT) atomicAdd(&scnt[s], 1u);
     };
 
-    auto consume = [&](int64_t c) {
-        const int buf = (int)(c % SPG_NBUF);
-        unsigned int n_in = __ldcg(&a.inbox_cnt[buf * G + me]);
-        if (n_in > (unsigned int)a.cap_rows) n_in = (unsigned int)a.cap_rows;
-        const longlong2* src = a.inbox + ((size_t)buf * G + me) * a.cap_rows;
-        for (unsigned int p = tid; p < n_in; p += SPG_THREADS) {
-            longlong2 row = __ldcg(src + p);
-            upsert(row.x, row.y);
+    unsigned long long n_in = a.bucket_cnt[me];
+    if (n_in > (unsigned long long)a.bucket_cap) n_in = (unsigned long long)a.bucket_cap;
+    const longlong2* src = a.bucket + (size_t)me * a.bucket_cap;
+    constexpr int U = 4;  // independent bucket loads in flight per thread
+    for (unsigned long long p0 = tid; p0 < n_in; p0 += (unsigned long long)U * SPG_THREADS) {
+        longlong2 row[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            unsigned long long p = p0 + (unsigned long long)u * SPG_THREADS;
+            row[u] = p < n_in ? __ldcs(src + p) : make_longlong2(EMPTY_KEY, 0);
         }
-        __syncthreads();
-        if (tid == 0) a.inbox_cnt[buf * G + me] = 0;  // ordered before this CTA's next arrive (fence + atomic)
-    };
-
-    bool ok = true;
-    if (a.n_chunks > 0) produce(0);
-    for (int64_t c = 0; c < a.n_chunks && ok; c++) {
-        if (c + 1 < a.n_chunks) produce(c + 1);
-        ok = wait_chunk(c);
-        if (ok) consume(c);
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (row[u].x != EMPTY_KEY) upsert(row[u].x, row[u].y);
     }
     __syncthreads();
     // flush the shared table into the state's global table
@@ -673,18 +661,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) groupby_spg_kernel(const __gri
         long long key = skeys[s];
         if (key == EMPTY_KEY) continue;
         unsigned long long sum = (unsigned long long)slo[s] | ((unsigned long long)shi[s] << 32);
-        unsigned long long cnt = scnt[s];
-        uint64_t sl = find_or_insert(a.tkeys, a.cap, key, a.counters, a.group_limit);
-        if (sl == ~0ull) {
-            unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
-            unsigned long long* r = a.retry + f * 4;
-            r[0] = (unsigned long long)key; r[1] = 1ull;
-            if (HAS_SUM && HAS_CNT) { r[2] = a.sum_first ? sum : cnt; r[3] = a.sum_first ? cnt : sum; }
-            else { r[2] = HAS_SUM ? sum : cnt; r[3] = 0; }
-            continue;
-        }
-        if (HAS_SUM) atomicAdd(a.acc_sum + sl, sum);
-        if (HAS_CNT) atomicAdd(a.acc_cnt + sl, cnt);
+        spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, sum, (unsigned long long)scnt[s]);
     }
 }
 
@@ -908,80 +885,80 @@ class GroupbyState {
     }
 
     // ---- SM-partitioned fast path (SPG) ----
-    static constexpr int SPG_TILE = 2048;
     static constexpr int64_t SPG_LAUNCH_ROWS = 1ll << 26;
-    DevBuf d_inbox, d_inbox_cnt, d_bar, d_retry;
-    int spg_ctas = 0, spg_ns = 0, spg_cap_rows = 0;
+    DevBuf d_bucket, d_bucket_cnt, d_retry;
+    int spg_owners = 0, spg_ns = 0;
     size_t spg_smem = 0;
     int spg_state = -1;  // -1 not probed, 0 unavailable/disabled, 1 ready
     int64_t spg_launches = 0, spg_retry_rows = 0;
     int64_t expected_groups_hint = 0;
-
-    template <bool S, bool C>
-    static const void* spg_func() { return (const void*)groupby_spg_kernel<S, C, SPG_TILE>; }
 
     bool spg_probe() {
         if (spg_state >= 0) return spg_state == 1;
         spg_state = 0;
         const char* env = getenv("B200_SPG");
         if (env && env[0] == '0') return false;
-        int coop = 0, max_smem = 0;
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        int max_smem = 0;
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-        if (!coop || sms > SPG_MAX_CTAS - 1) return false;
-        size_t fixed = (size_t)SPG_TILE * 17 + (3 * SPG_MAX_CTAS + 1 + 4) * 4 + 64;
-        if ((size_t)max_smem < fixed + 20 * 1024) return false;
-        spg_ns = (int)(((size_t)max_smem - fixed) / 20) & ~1;
-        spg_smem = (size_t)spg_ns * 20 + fixed;
-        const void* fns[3] = {spg_func<true, true>(), spg_func<true, false>(), spg_func<false, true>()};
-        for (auto f : fns) {
+        if (sms > SPG_MAX_OWNERS - 1 || max_smem < 64 * 1024) return false;
+        spg_ns = (int)(((size_t)max_smem - 64) / 20) & ~1;
+        spg_smem = (size_t)spg_ns * 20 + 16;
+        const void* fns[3] = {(const void*)spg_aggregate_kernel<true, true>, (const void*)spg_aggregate_kernel<true, false>,
+                              (const void*)spg_aggregate_kernel<false, true>};
+        for (auto f : fns)
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_smem) != cudaSuccess) { cudaGetLastError(); return false; }
-            int nb = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, SPG_THREADS, spg_smem) != cudaSuccess || nb < 1) { cudaGetLastError(); return false; }
-        }
-        spg_ctas = sms;
-        // rows per owner per chunk: mean TILE, sd sqrt(TILE) for uniform keys; leave 25 % head room
-        spg_cap_rows = (SPG_TILE + SPG_TILE / 4 + 63) & ~63;
-        d_inbox.alloc((size_t)SPG_NBUF * spg_ctas * spg_cap_rows * 16);
-        d_inbox_cnt.alloc((size_t)SPG_NBUF * spg_ctas * 4);
+        const void* pf[3] = {(const void*)spg_partition_kernel<true, true>, (const void*)spg_partition_kernel<true, false>,
+                             (const void*)spg_partition_kernel<false, true>};
+        for (auto f : pf)
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_part_smem()) != cudaSuccess) { cudaGetLastError(); return false; }
+        spg_owners = sms;  // one owner (bucket + shared table) per SM
+        d_bucket_cnt.alloc((size_t)spg_owners * 8);
         spg_state = 1;
         return true;
     }
 
-    // groups the shared-memory tables of all CTAs can hold together (7/8 of the slots, see occ_limit)
-    int64_t spg_group_capacity() const { return (int64_t)spg_ctas * (spg_ns - spg_ns / 8); }
+    static size_t spg_part_smem() { return (size_t)SPG_TILE * 17 + SPG_MAX_OWNERS * 8 + (2 * SPG_MAX_OWNERS + 4) * 4 + 64; }
+    // groups the shared-memory tables of all owners can hold together (7/8 of the slots, see occ_limit)
+    int64_t spg_group_capacity() const { return (int64_t)spg_owners * (spg_ns - spg_ns / 8); }
 
     void consume_spg(const long long* keys, const long long* vals, int64_t n, int sum_j, int cnt_j) {
         for (int64_t r0 = 0; r0 < n; r0 += SPG_LAUNCH_ROWS) {
             int64_t rows = std::min(SPG_LAUNCH_ROWS, n - r0);
-            // the flush inserts at most ctas * ns groups; keep that much room so the common case never retries
-            while ((int64_t)(cap / 2) < n_groups_bound + (int64_t)spg_ctas * spg_ns + 1024) grow(cap * 2);
-            int64_t per_chunk = (int64_t)spg_ctas * SPG_TILE;
-            int64_t n_chunks = (rows + per_chunk - 1) / per_chunk;
-            d_bar.ensure((size_t)n_chunks * 4);
-            d_retry.ensure(((size_t)rows + (size_t)spg_ctas * spg_ns) * 32);
-            B200_CUDA(cudaMemsetAsync(d_bar.p, 0, (size_t)n_chunks * 4, stream));
-            B200_CUDA(cudaMemsetAsync(d_inbox_cnt.p, 0, (size_t)SPG_NBUF * spg_ctas * 4, stream));
-            B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8, 0, 8, stream));       // retry rows
-            B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 5 * 8, 0, 8, stream));   // error flag
+            // the flush inserts at most owners * ns groups; keep that much room so the common case never retries
+            while ((int64_t)(cap / 2) < n_groups_bound + (int64_t)spg_owners * spg_ns + 1024) grow(cap * 2);
+            // uniform keys put rows / owners rows in every bucket (sd = sqrt of that); 12.5 % + 4096 rows head room,
+            // anything beyond (skew) takes the direct path inside K1
+            int64_t bucket_cap = (rows / spg_owners) + (rows / spg_owners) / 8 + 4096;
+            d_bucket.ensure((size_t)spg_owners * bucket_cap * 16);
+            d_retry.ensure(((size_t)rows + (size_t)spg_owners * spg_ns) * 32);
+            B200_CUDA(cudaMemsetAsync(d_bucket_cnt.p, 0, (size_t)spg_owners * 8, stream));
+            B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8, 0, 8, stream));  // retry rows
             SpgArgs a{};
-            a.keys = keys + r0; a.vals = vals ? vals + r0 : nullptr; a.n_rows = rows;
+            a.keys = keys + r0; a.vals = vals ? vals + r0 : nullptr; a.n_rows = rows; a.n_owners = spg_owners;
             a.tkeys = d_keys.as<long long>(); a.cap = cap;
             a.acc_sum = sum_j >= 0 ? d_a0[sum_j].as<unsigned long long>() : nullptr;
             a.acc_cnt = cnt_j >= 0 ? d_a0[cnt_j].as<unsigned long long>() : nullptr;
             a.counters = d_counters.as<long long>(); a.group_limit = (long long)(cap / 2);
-            a.inbox = d_inbox.as<longlong2>(); a.inbox_cnt = d_inbox_cnt.as<unsigned int>(); a.bar = d_bar.as<unsigned int>();
-            a.cap_rows = spg_cap_rows; a.n_chunks = n_chunks; a.retry = d_retry.as<unsigned long long>();
+            a.bucket = d_bucket.as<longlong2>(); a.bucket_cnt = d_bucket_cnt.as<unsigned long long>(); a.bucket_cap = bucket_cap;
+            a.retry = d_retry.as<unsigned long long>();
             a.sum_first = (sum_j >= 0 && cnt_j >= 0 && sum_j < cnt_j) ? 1 : 0; a.ns = spg_ns;
-            const void* f = (sum_j >= 0 && cnt_j >= 0) ? spg_func<true, true>() : (sum_j >= 0 ? spg_func<true, false>() : spg_func<false, true>());
-            void* params[1] = {(void*)&a};
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (profiling) { B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1)); B200_CUDA(cudaEventRecord(ev0, stream)); }
-            B200_CUDA(cudaLaunchCooperativeKernel(f, dim3(spg_ctas), dim3(SPG_THREADS), params, spg_smem, stream));
+            int g1 = (int)std::min<int64_t>((int64_t)sms * 2, (rows + SPG_TILE - 1) / SPG_TILE);
+            if (sum_j >= 0 && cnt_j >= 0) {
+                spg_partition_kernel<true, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
+                spg_aggregate_kernel<true, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+            } else if (sum_j >= 0) {
+                spg_partition_kernel<true, false><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
+                spg_aggregate_kernel<true, false><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+            } else {
+                spg_partition_kernel<false, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
+                spg_aggregate_kernel<false, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+            }
+            B200_CUDA(cudaGetLastError());
             if (ev0) { B200_CUDA(cudaEventRecord(ev1, stream)); prof_events.emplace_back(ev0, ev1); }
-            launches++; consume_launches++; spg_launches++;
+            launches += 2; consume_launches++; spg_launches++;
             read_counters();
-            if (h_counters[5]) throw Error("b200 groupby: SPG kernel aborted (inter-CTA barrier timed out); set B200_SPG=0 to use the direct kernel");
             // rows / partials that found the global table full: grow, then merge them like received partial rows
             while (h_counters[1] > 0) {
                 int64_t nr = h_counters[1];
