@@ -169,4 +169,27 @@ struct DevBuf {
     template <typename T> T* as() const { return (T*)p; }
 };
 
+// Scratch buffers (bucket / retry / fail lists: up to GBs) come from a process-wide per-device pool and go back to
+// it when a state dies, so creating an operator state per query does not pay cudaMalloc / cudaFree of gigabytes
+// (cudaFree of multi-GB blocks is synchronous and costs tens of milliseconds).
+void* scratch_acquire(int device, size_t bytes, size_t* got);
+void scratch_release(int device, void* p, size_t bytes);
+struct PooledBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int device = 0;
+    PooledBuf() = default;
+    PooledBuf(const PooledBuf&) = delete;
+    PooledBuf& operator=(const PooledBuf&) = delete;
+    ~PooledBuf() { release(); }
+    void release() { if (p) scratch_release(device, p, bytes); p = nullptr; bytes = 0; }
+    void ensure(int dev, size_t n) {
+        if (n <= bytes) return;
+        release();
+        device = dev;
+        p = scratch_acquire(dev, n, &bytes);
+    }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
 }  // namespace b200

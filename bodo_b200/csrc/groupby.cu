@@ -11,6 +11,8 @@
 //     _groupby.cpp:3309-3341, without the partition split);
 //   * finalize compacts occupied slots and evaluates the output columns (mean_eval etc.).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -468,8 +470,9 @@ __global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
 // inside the same kernels; rows that cannot even be inserted there (global table at its limit) are appended to
 // a retry list in the partial-aggregate wire format and replayed by combine_partials_kernel after the table grew.
 constexpr int SPG_THREADS = 1024;   // K2 (aggregate) threads per CTA
-constexpr int SPG_PTHREADS = 512;   // K1 (partition) threads per CTA, 2 CTAs per SM
-constexpr int SPG_TILE = 4096;
+constexpr int SPG_PTHREADS = 256;   // K1 (partition) threads per CTA
+constexpr int SPG_PCTAS = 4;        // K1 CTAs per SM (more independent CTAs = barrier / load stalls overlap)
+constexpr int SPG_TILE = 2048;
 constexpr int SPG_MAX_OWNERS = 256;
 
 struct SpgArgs {
@@ -489,6 +492,7 @@ struct SpgArgs {
     unsigned long long* bucket_cnt;  // [n_owners] rows appended (may exceed bucket_cap: the excess went the direct way)
     long long bucket_cap;
     unsigned long long* retry;  // partial-aggregate rows [key][1][a0 of func 0][a0 of func 1]
+    long long* retry_ctr;       // number of rows in `retry`
     int sum_first;              // order of the two accumulators in the wire format
     int ns;                     // shared-memory table slots (K2)
 };
@@ -504,7 +508,7 @@ __device__ __forceinline__ unsigned int spg_slot(uint64_t h, int ns) { return __
 
 template <bool HAS_SUM, bool HAS_CNT>
 __device__ __forceinline__ void spg_retry_row(const SpgArgs& a, long long key, unsigned long long sum, unsigned long long cnt) {
-    unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
+    unsigned long long f = atomicAdd((unsigned long long*)a.retry_ctr, 1ull);
     unsigned long long* r = a.retry + f * 4;
     r[0] = (unsigned long long)key; r[1] = 1ull;
     if (HAS_SUM && HAS_CNT) { r[2] = a.sum_first ? sum : cnt; r[3] = a.sum_first ? cnt : sum; }
@@ -524,7 +528,7 @@ __device__ __forceinline__ void spg_direct_apply(const SpgArgs& a, long long key
 
 // K1: partition rows into owner buckets. grid = persistent (2 CTAs / SM), tiles are taken grid-stride.
 template <bool HAS_SUM, bool HAS_CNT>
-__global__ void __launch_bounds__(SPG_PTHREADS, 2) spg_partition_kernel(const __grid_constant__ SpgArgs a) {
+__global__ void __launch_bounds__(SPG_PTHREADS, SPG_PCTAS) spg_partition_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     longlong2* stage = (longlong2*)smem_raw;                                   // SPG_TILE x 16
     unsigned long long* gbase = (unsigned long long*)(stage + SPG_TILE);      // SPG_MAX_OWNERS x 8
@@ -535,6 +539,8 @@ __global__ void __launch_bounds__(SPG_PTHREADS, 2) spg_partition_kernel(const __
     constexpr int ROWS = SPG_TILE / SPG_PTHREADS;  // 8 rows per thread per tile, as 4 adjacent pairs
     constexpr int PAIRS = ROWS / 2;
     const int64_t n_tiles = (a.n_rows + SPG_TILE - 1) / SPG_TILE;
+    for (int j = tid; j < G; j += SPG_PTHREADS) hist[j] = 0;
+    __syncthreads();
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int64_t r0 = t * SPG_TILE;
         long long k[ROWS], v[ROWS];
@@ -554,8 +560,6 @@ __global__ void __launch_bounds__(SPG_PTHREADS, 2) spg_partition_kernel(const __
                 k[2 * j + 1] = 0; v[2 * j + 1] = 0; o[2 * j + 1] = -1;
             } else { k[2 * j] = k[2 * j + 1] = 0; v[2 * j] = v[2 * j + 1] = 0; o[2 * j] = o[2 * j + 1] = -1; }
         }
-        for (int j = tid; j < G; j += SPG_PTHREADS) hist[j] = 0;
-        __syncthreads();
 #pragma unroll
         for (int r = 0; r < ROWS; r++) {
             if (o[r] < 0) continue;
@@ -595,6 +599,7 @@ __global__ void __launch_bounds__(SPG_PTHREADS, 2) spg_partition_kernel(const __
             if (off < (unsigned long long)a.bucket_cap) a.bucket[(size_t)ow * a.bucket_cap + off] = row;
             else spg_direct_apply<HAS_SUM, HAS_CNT>(a, row.x, (unsigned long long)row.y, 1ull);  // bucket full (skew): direct path
         }
+        for (int j = tid; j < G; j += SPG_PTHREADS) hist[j] = 0;  // for the next tile (gbase/lbase were consumed above)
         __syncthreads();
     }
 }
@@ -643,7 +648,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     unsigned long long n_in = a.bucket_cnt[me];
     if (n_in > (unsigned long long)a.bucket_cap) n_in = (unsigned long long)a.bucket_cap;
     const longlong2* src = a.bucket + (size_t)me * a.bucket_cap;
-    constexpr int U = 4;  // independent bucket loads in flight per thread
+    constexpr int U = 4;  // independent bucket loads in flight per thread (8 measured slower: 62 registers)
     for (unsigned long long p0 = tid; p0 < n_in; p0 += (unsigned long long)U * SPG_THREADS) {
         longlong2 row[U];
 #pragma unroll
@@ -700,7 +705,7 @@ class GroupbyState {
     std::vector<DevBuf> d_a0, d_a1;
     DevBuf d_counters;
     long long* h_counters = nullptr;  // pinned
-    DevBuf d_fail;
+    PooledBuf d_fail;
     int64_t n_groups = 0;
 
     // host-input staging (double buffered, per used column)
@@ -717,6 +722,9 @@ class GroupbyState {
     std::vector<long long> h_dest_count;
     int64_t packed_rows = 0;
 
+    // host-side time accounting (printed at delete when B200_TRACE is set)
+    double t_ctor = 0, t_grow = 0, t_alloc = 0, t_spg = 0, t_finalize = 0;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
     // metrics
     int64_t rows_consumed = 0, rebuilds = 0, launches = 0, fail_rows = 0;
     bool build_done = false;
@@ -798,16 +806,23 @@ class GroupbyState {
         uint64_t want = 1ull << 16;
         if (expected_groups > 0) { while (want < (uint64_t)expected_groups * 2) want <<= 1; }
         else want = 1ull << 21;
+        double t0 = now();
         alloc_table(want, d_keys, d_a0, d_a1);
         cap = want;
+        t_ctor = now() - t0;
     }
 
     ~GroupbyState() {
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
+        if (getenv("B200_TRACE"))
+            fprintf(stderr, "[b200 groupby state] ctor %.3f ms, grow %.3f ms (%lld rebuilds), spg alloc %.3f ms, spg loop %.3f ms, finalize %.3f ms, cap %llu\n",
+                    t_ctor * 1e3, t_grow * 1e3, (long long)rebuilds, t_alloc * 1e3, t_spg * 1e3, t_finalize * 1e3, (unsigned long long)cap);
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         for (int b = 0; b < 2; b++) { if (stage_free[b]) cudaEventDestroy(stage_free[b]); if (stage_ready[b]) cudaEventDestroy(stage_ready[b]); }
         if (h_counters) cudaFreeHost(h_counters);
+        if (h_spg) cudaFreeHost(h_spg);
+        for (int b = 0; b < 2; b++) if (spg_ev[b]) cudaEventDestroy(spg_ev[b]);
         for (auto& pr : prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     }
 
@@ -841,6 +856,8 @@ class GroupbyState {
     }
 
     void grow(uint64_t new_cap) {
+        double t0 = now();
+        struct Acc { double& t; double t0; ~Acc() { t += now() - t0; } } acc{t_grow, t0};
         DevBuf nk; std::vector<DevBuf> na0(n_funcs), na1(n_funcs);
         alloc_table(new_cap, nk, na0, na1);
         RehashArgs ra{};
@@ -886,7 +903,8 @@ class GroupbyState {
 
     // ---- SM-partitioned fast path (SPG) ----
     static constexpr int64_t SPG_LAUNCH_ROWS = 1ll << 26;
-    DevBuf d_bucket, d_bucket_cnt, d_retry;
+    PooledBuf d_bucket;
+    DevBuf d_bucket_cnt;
     int spg_owners = 0, spg_ns = 0;
     size_t spg_smem = 0;
     int spg_state = -1;  // -1 not probed, 0 unavailable/disabled, 1 ready
@@ -921,30 +939,86 @@ class GroupbyState {
     // groups the shared-memory tables of all owners can hold together (7/8 of the slots, see occ_limit)
     int64_t spg_group_capacity() const { return (int64_t)spg_owners * (spg_ns - spg_ns / 8); }
 
+    // One SPG launch pair in flight while the host inspects the previous one (two retry lists / counter slots), so
+    // the GPU never idles on the host's counter read-back.
+    PooledBuf d_retry2[2];
+    long long* h_spg = nullptr;  // pinned: [slot][8] counter snapshots
+    cudaEvent_t spg_ev[2] = {nullptr, nullptr};
+
+    void spg_finish(int slot, int sum_j, int cnt_j) {
+        B200_CUDA(cudaEventSynchronize(spg_ev[slot]));
+        const long long* hc = h_spg + slot * 8;
+        n_groups = hc[0];
+        int64_t nr = hc[1 + 5 * slot];  // retry rows of that launch: counters[1] (slot 0) / counters[6] (slot 1)
+        while (nr > 0) {
+            // rows / partials that found the global table full: grow, then merge them like received partial rows
+            spg_retry_rows += nr;
+            B200_CUDA(cudaStreamSynchronize(stream));  // the other in-flight launch uses the table we are about to replace
+            read_counters();
+            uint64_t nc = cap;
+            int64_t pending = h_counters[1] + h_counters[6];
+            while (nc < 2ull * (uint64_t)(n_groups + pending + (int64_t)spg_owners * spg_ns)) nc <<= 1;
+            if (nc == cap) nc <<= 1;
+            grow(nc);
+            for (int sl = 0; sl < 2; sl++) {
+                int64_t cnt = h_counters[1 + 5 * sl];
+                if (cnt == 0) continue;
+                B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8 * (1 + 5 * sl), 0, 8, stream));
+                CombineArgs c{};
+                c.in = d_retry2[sl].as<unsigned long long>(); c.n_rows = cnt; c.row_words = 4;
+                d_fail.ensure(device, (size_t)cnt * 4);
+                c.tkeys = d_keys.as<long long>(); c.cap = cap; c.counters = d_counters.as<long long>(); c.group_limit = (long long)(cap / 2);
+                c.fail_list = d_fail.as<uint32_t>(); c.index_list = nullptr; c.n_ops = 0;  // cannot fail: the table was grown for all pending rows
+                // wire order = function order of the (at most two) accumulators
+                int order[2] = {sum_j, cnt_j};
+                if (sum_j >= 0 && cnt_j >= 0 && cnt_j < sum_j) std::swap(order[0], order[1]);
+                if (order[0] < 0) std::swap(order[0], order[1]);
+                for (int q = 0; q < 2; q++) if (order[q] >= 0) { c.kinds[c.n_ops] = K_SUM_I64; c.a0[c.n_ops] = d_a0[order[q]].p; c.a1[c.n_ops] = nullptr; c.n_ops++; }
+                combine_partials_kernel<<<grid_for(cnt), 256, 0, stream>>>(c);
+                launches++;
+                B200_CUDA(cudaGetLastError());
+            }
+            read_counters();
+            nr = 0;
+        }
+    }
+
     void consume_spg(const long long* keys, const long long* vals, int64_t n, int sum_j, int cnt_j) {
-        for (int64_t r0 = 0; r0 < n; r0 += SPG_LAUNCH_ROWS) {
+        if (!h_spg) {
+            B200_CUDA(cudaMallocHost((void**)&h_spg, 16 * sizeof(long long)));
+            for (int b = 0; b < 2; b++) B200_CUDA(cudaEventCreateWithFlags(&spg_ev[b], cudaEventDisableTiming));
+        }
+        double tspg0 = now();
+        struct Acc2 { double& t; double t0; ~Acc2() { t += now() - t0; } } acc2{t_spg, tspg0};
+        read_counters();  // exact group count before the first launch
+        n_groups_bound = n_groups;
+        int64_t li = 0;
+        for (int64_t r0 = 0; r0 < n; r0 += SPG_LAUNCH_ROWS, li++) {
+            int slot = (int)(li & 1);
             int64_t rows = std::min(SPG_LAUNCH_ROWS, n - r0);
-            // the flush inserts at most owners * ns groups; keep that much room so the common case never retries
-            while ((int64_t)(cap / 2) < n_groups_bound + (int64_t)spg_owners * spg_ns + 1024) grow(cap * 2);
+            // no pre-growing: a flush that finds the global table at its limit lands in the retry list and is merged
+            // after the table grew (spg_finish), exactly like rows of the direct path
             // uniform keys put rows / owners rows in every bucket (sd = sqrt of that); 12.5 % + 4096 rows head room,
             // anything beyond (skew) takes the direct path inside K1
             int64_t bucket_cap = (rows / spg_owners) + (rows / spg_owners) / 8 + 4096;
-            d_bucket.ensure((size_t)spg_owners * bucket_cap * 16);
-            d_retry.ensure(((size_t)rows + (size_t)spg_owners * spg_ns) * 32);
+            double ta = now();
+            d_bucket.ensure(device, (size_t)spg_owners * bucket_cap * 16);  // K2 of the previous launch precedes K1 of this one in stream order
+            d_retry2[slot].ensure(device, ((size_t)rows + (size_t)spg_owners * spg_ns) * 32);
+            t_alloc += now() - ta;
             B200_CUDA(cudaMemsetAsync(d_bucket_cnt.p, 0, (size_t)spg_owners * 8, stream));
-            B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8, 0, 8, stream));  // retry rows
             SpgArgs a{};
             a.keys = keys + r0; a.vals = vals ? vals + r0 : nullptr; a.n_rows = rows; a.n_owners = spg_owners;
             a.tkeys = d_keys.as<long long>(); a.cap = cap;
             a.acc_sum = sum_j >= 0 ? d_a0[sum_j].as<unsigned long long>() : nullptr;
             a.acc_cnt = cnt_j >= 0 ? d_a0[cnt_j].as<unsigned long long>() : nullptr;
             a.counters = d_counters.as<long long>(); a.group_limit = (long long)(cap / 2);
+            a.retry_ctr = d_counters.as<long long>() + 1 + 5 * slot;
             a.bucket = d_bucket.as<longlong2>(); a.bucket_cnt = d_bucket_cnt.as<unsigned long long>(); a.bucket_cap = bucket_cap;
-            a.retry = d_retry.as<unsigned long long>();
+            a.retry = d_retry2[slot].as<unsigned long long>();
             a.sum_first = (sum_j >= 0 && cnt_j >= 0 && sum_j < cnt_j) ? 1 : 0; a.ns = spg_ns;
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (profiling) { B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1)); B200_CUDA(cudaEventRecord(ev0, stream)); }
-            int g1 = (int)std::min<int64_t>((int64_t)sms * 2, (rows + SPG_TILE - 1) / SPG_TILE);
+            int g1 = (int)std::min<int64_t>((int64_t)sms * SPG_PCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
             if (sum_j >= 0 && cnt_j >= 0) {
                 spg_partition_kernel<true, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
                 spg_aggregate_kernel<true, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
@@ -957,34 +1031,15 @@ class GroupbyState {
             }
             B200_CUDA(cudaGetLastError());
             if (ev0) { B200_CUDA(cudaEventRecord(ev1, stream)); prof_events.emplace_back(ev0, ev1); }
+            B200_CUDA(cudaMemcpyAsync(h_spg + slot * 8, d_counters.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+            B200_CUDA(cudaEventRecord(spg_ev[slot], stream));
             launches += 2; consume_launches++; spg_launches++;
-            read_counters();
-            // rows / partials that found the global table full: grow, then merge them like received partial rows
-            while (h_counters[1] > 0) {
-                int64_t nr = h_counters[1];
-                spg_retry_rows += nr;
-                uint64_t nc = cap;
-                while (nc < 2ull * (uint64_t)(n_groups + nr)) nc <<= 1;
-                if (nc == cap) nc <<= 1;
-                grow(nc);
-                B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8, 0, 8, stream));
-                CombineArgs c{};
-                c.in = d_retry.as<unsigned long long>(); c.n_rows = nr; c.row_words = 4;
-                c.tkeys = d_keys.as<long long>(); c.cap = cap; c.counters = d_counters.as<long long>(); c.group_limit = (long long)(cap / 2);
-                c.fail_list = nullptr; c.index_list = nullptr; c.n_ops = 0;
-                // wire order = function order of the (at most two) accumulators
-                int order[2] = {sum_j, cnt_j};
-                if (sum_j >= 0 && cnt_j >= 0 && cnt_j < sum_j) std::swap(order[0], order[1]);
-                if (order[0] < 0) std::swap(order[0], order[1]);
-                for (int q = 0; q < 2; q++) if (order[q] >= 0) { c.kinds[c.n_ops] = K_SUM_I64; c.a0[c.n_ops] = d_a0[order[q]].p; c.a1[c.n_ops] = nullptr; c.n_ops++; }
-                combine_partials_kernel<<<grid_for(nr), 256, 0, stream>>>(c);
-                launches++;
-                B200_CUDA(cudaGetLastError());
-                read_counters();
-            }
-            n_groups_bound = n_groups;
             rows_consumed += rows;
+            if (li > 0) spg_finish(1 - slot, sum_j, cnt_j);  // inspect the previous launch while this one runs
         }
+        if (li > 0) spg_finish((int)((li - 1) & 1), sum_j, cnt_j);
+        read_counters();
+        n_groups_bound = n_groups;
     }
 
     // Consume rows [0, n) of device-resident columns.
@@ -1032,7 +1087,7 @@ class GroupbyState {
     void consume_direct(const std::vector<const void*>& data, const std::vector<const uint8_t*>& valid, int64_t n, bool fast, int sum_j,
                         int cnt_j, int vcol, bool force_count) {
         bool could_fail = force_count || (int64_t)(cap / 2) - n_groups_bound < n;
-        if (could_fail) d_fail.ensure((size_t)n * 4);
+        if (could_fail) d_fail.ensure(device, (size_t)n * 4);
         // table pointers are looked up at launch time: grow() replaces them between a launch and its replay
         auto launch = [&](const uint32_t* index_list, int64_t rows) {
             long long* ctr = d_counters.as<long long>();
@@ -1168,6 +1223,8 @@ class GroupbyState {
 
     int64_t finalize() {
         if (finalized) return n_out;
+        double tf0 = now();
+        struct Acc3 { double& t; double t0; ~Acc3() { t += now() - t0; } } acc3{t_finalize, tf0};
         B200_CUDA(cudaSetDevice(device));
         compact();
         EvalArgs e{};
@@ -1249,7 +1306,7 @@ class GroupbyState {
         if (n_rows == 0) return;
         B200_REQUIRE(n_rows < (1ll << 32), "b200 groupby: too many partial rows in one combine call");
         bool could_fail = (int64_t)(cap / 2) - n_groups_bound < n_rows;
-        if (could_fail) d_fail.ensure((size_t)n_rows * 4);
+        if (could_fail) d_fail.ensure(device, (size_t)n_rows * 4);
         auto launch = [&](const uint32_t* index_list, int64_t rows) {
             CombineArgs c{};
             c.in = (const unsigned long long*)recv; c.n_rows = rows; c.row_words = 2 + acc_count();

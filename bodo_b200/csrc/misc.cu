@@ -1,7 +1,53 @@
 // misc.cu — error reporting, runtime probes, raw memory helpers and the synthetic-table generator.
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace b200 {
+namespace {
+struct PoolEntry { void* p; size_t bytes; };
+std::mutex g_pool_mutex;
+std::vector<PoolEntry> g_pool[64];
+}  // namespace
+
+void* scratch_acquire(int device, size_t bytes, size_t* got) {
+    if (bytes == 0) bytes = 8;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        auto& v = g_pool[device & 63];
+        int best = -1;
+        for (int i = 0; i < (int)v.size(); i++)
+            if (v[i].bytes >= bytes && (best < 0 || v[i].bytes < v[best].bytes)) best = i;
+        if (best >= 0) {
+            PoolEntry e = v[best];
+            v.erase(v.begin() + best);
+            *got = e.bytes;
+            return e.p;
+        }
+    }
+    void* p = nullptr;
+    B200_CUDA(cudaSetDevice(device));
+    cudaError_t err = cudaMalloc(&p, bytes);
+    if (err != cudaSuccess) {
+        // out of memory: give the pooled blocks back to the driver and retry once
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mutex);
+            for (auto& e : g_pool[device & 63]) cudaFree(e.p);
+            g_pool[device & 63].clear();
+        }
+        B200_CUDA(cudaMalloc(&p, bytes));
+    }
+    *got = bytes;
+    return p;
+}
+void scratch_release(int device, void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    g_pool[device & 63].push_back({p, bytes});
+}
+
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
