@@ -144,52 +144,39 @@ inline int num_sms(int device) {
     return n > 0 ? n : 148;
 }
 
-// RAII device buffer on a fixed device (plain cudaMalloc: allocations happen at state set-up / growth
-// time, never per batch on the steady-state path).
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
-        return *this;
-    }
-    ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
-    void alloc(size_t n) {
-        release();
-        if (n == 0) n = 8;
-        B200_CUDA(cudaMalloc(&p, n));
-        bytes = n;
-    }
-    void ensure(size_t n) { if (n > bytes) alloc(n); }
-    template <typename T> T* as() const { return (T*)p; }
-};
-
 // Scratch buffers (bucket / retry / fail lists: up to GBs) come from a process-wide per-device pool and go back to
 // it when a state dies, so creating an operator state per query does not pay cudaMalloc / cudaFree of gigabytes
 // (cudaFree of multi-GB blocks is synchronous and costs tens of milliseconds).
 void* scratch_acquire(int device, size_t bytes, size_t* got);
 void scratch_release(int device, void* p, size_t bytes);
-struct PooledBuf {
+void* pinned_acquire(size_t bytes);   // small pinned host blocks (counter mirrors), pooled for the same reason
+void pinned_release(void* p, size_t bytes);
+
+// RAII device buffer drawn from the pool of the CURRENT device (states call cudaSetDevice first).
+struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
-    int device = 0;
-    PooledBuf() = default;
-    PooledBuf(const PooledBuf&) = delete;
-    PooledBuf& operator=(const PooledBuf&) = delete;
-    ~PooledBuf() { release(); }
-    void release() { if (p) scratch_release(device, p, bytes); p = nullptr; bytes = 0; }
-    void ensure(int dev, size_t n) {
-        if (n <= bytes) return;
-        release();
-        device = dev;
-        p = scratch_acquire(dev, n, &bytes);
+    int device = -1;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), device(o.device) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; device = o.device; o.p = nullptr; o.bytes = 0; }
+        return *this;
     }
+    ~DevBuf() { release(); }
+    void release() { if (p) scratch_release(device, p, bytes); p = nullptr; bytes = 0; }
+    void alloc(size_t n) {
+        release();
+        if (n == 0) n = 8;
+        B200_CUDA(cudaGetDevice(&device));
+        p = scratch_acquire(device, n, &bytes);
+    }
+    void ensure(size_t n) { if (n > bytes) alloc(n); }
+    void ensure(int /*dev*/, size_t n) { ensure(n); }
     template <typename T> T* as() const { return (T*)p; }
 };
+using PooledBuf = DevBuf;
 
 }  // namespace b200

@@ -801,7 +801,7 @@ class GroupbyState {
         d_out_data.resize(n_funcs); d_out_valid.resize(n_funcs);
         d_counters.alloc(8 * sizeof(long long));
         B200_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(long long), stream));
-        B200_CUDA(cudaMallocHost((void**)&h_counters, 8 * sizeof(long long)));
+        h_counters = (long long*)pinned_acquire(8 * sizeof(long long));
         expected_groups_hint = expected_groups > 0 ? expected_groups : 0;
         uint64_t want = 1ull << 16;
         if (expected_groups > 0) { while (want < (uint64_t)expected_groups * 2) want <<= 1; }
@@ -820,8 +820,8 @@ class GroupbyState {
                     t_ctor * 1e3, t_grow * 1e3, (long long)rebuilds, t_alloc * 1e3, t_spg * 1e3, t_finalize * 1e3, (unsigned long long)cap);
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         for (int b = 0; b < 2; b++) { if (stage_free[b]) cudaEventDestroy(stage_free[b]); if (stage_ready[b]) cudaEventDestroy(stage_ready[b]); }
-        if (h_counters) cudaFreeHost(h_counters);
-        if (h_spg) cudaFreeHost(h_spg);
+        pinned_release(h_counters, 8 * sizeof(long long));
+        pinned_release(h_spg, 16 * sizeof(long long));
         for (int b = 0; b < 2; b++) if (spg_ev[b]) cudaEventDestroy(spg_ev[b]);
         for (auto& pr : prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     }
@@ -985,7 +985,7 @@ class GroupbyState {
 
     void consume_spg(const long long* keys, const long long* vals, int64_t n, int sum_j, int cnt_j) {
         if (!h_spg) {
-            B200_CUDA(cudaMallocHost((void**)&h_spg, 16 * sizeof(long long)));
+            h_spg = (long long*)pinned_acquire(16 * sizeof(long long));
             for (int b = 0; b < 2; b++) B200_CUDA(cudaEventCreateWithFlags(&spg_ev[b], cudaEventDisableTiming));
         }
         double tspg0 = now();

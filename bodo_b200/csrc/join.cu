@@ -83,10 +83,10 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const uint32_t* in, int
 struct Scanner {
     DevBuf sums, total;
     unsigned long long* h_total = nullptr;
-    ~Scanner() { if (h_total) cudaFreeHost(h_total); }
+    ~Scanner() { pinned_release(h_total, 8); }
     // out[i] = sum_{j<i} in[j]; returns the grand total (synchronises the stream)
     unsigned long long run(const uint32_t* in, int64_t n, unsigned long long* out, cudaStream_t st, int64_t* launches) {
-        if (!h_total) B200_CUDA(cudaMallocHost((void**)&h_total, 8));
+        if (!h_total) h_total = (unsigned long long*)pinned_acquire(8);
         if (n == 0) return 0;
         int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
         sums.ensure((size_t)nb * 8);

@@ -16,9 +16,11 @@ void* scratch_acquire(int device, size_t bytes, size_t* got) {
     {
         std::lock_guard<std::mutex> lk(g_pool_mutex);
         auto& v = g_pool[device & 63];
+        // best fit, but never hand out a block more than 2x (+1 MiB) larger than asked for
+        size_t limit = bytes * 2 + (1u << 20);
         int best = -1;
         for (int i = 0; i < (int)v.size(); i++)
-            if (v[i].bytes >= bytes && (best < 0 || v[i].bytes < v[best].bytes)) best = i;
+            if (v[i].bytes >= bytes && v[i].bytes <= limit && (best < 0 || v[i].bytes < v[best].bytes)) best = i;
         if (best >= 0) {
             PoolEntry e = v[best];
             v.erase(v.begin() + best);
@@ -46,6 +48,23 @@ void scratch_release(int device, void* p, size_t bytes) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(g_pool_mutex);
     g_pool[device & 63].push_back({p, bytes});
+}
+
+namespace { std::vector<PoolEntry> g_pinned; }
+void* pinned_acquire(size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        for (size_t i = 0; i < g_pinned.size(); i++)
+            if (g_pinned[i].bytes >= bytes) { void* p = g_pinned[i].p; g_pinned.erase(g_pinned.begin() + i); return p; }
+    }
+    void* p = nullptr;
+    B200_CUDA(cudaMallocHost(&p, bytes < 256 ? 256 : bytes));
+    return p;
+}
+void pinned_release(void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    g_pinned.push_back({p, bytes < 256 ? 256 : bytes});
 }
 
 static thread_local std::string g_last_error;
