@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 METRIC = "groupby-agg rows/sec"
 UNIT = "rows/s"
 BYTES_PER_ROW = 16  # algorithmic bytes of the hash-aggregate scan
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/):
+# filled in from profiles/r01_*.txt for the 2^26-row launch of the default workload; None = not captured
+TRAFFIC_PER_LAUNCH = {"spg": None, "direct": None}
 
 
 def parse_args():
@@ -225,6 +228,7 @@ def main():
             if profile:
                 stats["consume_us"] = G.get_metric(st, 6)
                 stats["consume_launches"] = G.get_metric(st, 7)
+                stats["spg_launches"] = G.get_metric(st, 8)
         G.delete_groupby_state(st)
         return res
 
@@ -267,7 +271,9 @@ def main():
     n_launch = max(stats.get("consume_launches", 1), 1)
     achieved = (BYTES_PER_ROW * n_local / 1e9) / (kern_us * 1e-6) if kern_us else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "peak_kind": peak_kind, "kernel": "groupby_consume_i64_sumcount_kernel<true,true>",
+                "traffic": TRAFFIC_PER_LAUNCH.get("spg" if stats.get("spg_launches") else "direct"), "peak_kind": peak_kind,
+                "kernel": ("spg_partition_kernel<true,true> + spg_aggregate_kernel<true,true> (one launch = the pair)"
+                           if stats.get("spg_launches") else "groupby_consume_i64_sumcount_kernel<true,true>"),
                 "launches_per_step": n_launch, "avg_launch_ms": kern_us / 1e3 / n_launch,
                 "algorithmic_bytes_per_launch": BYTES_PER_ROW * n_local / n_launch}
 
