@@ -32,7 +32,10 @@ UNIT = "rows/s"
 BYTES_PER_ROW = 16  # algorithmic bytes of the hash-aggregate scan
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/):
 # filled in from profiles/r01_*.txt for the 2^26-row launch of the default workload; None = not captured
-TRAFFIC_PER_LAUNCH = {"spg": None, "direct": None}
+# spg: profiles/r01_spg_ncu_summary.txt, K1 1.074+1.019 GB + K2 1.123+0.004 GB per 2^26-row launch pair (3x the
+# algorithmic 1.074 GB by design: rows are written to and re-read from owner buckets).
+# direct: profiles/r01_direct_ncu_summary.txt (2^27-row launch, bucketized variant): 10.99 + 0.18 GB.
+TRAFFIC_PER_LAUNCH = {"spg": 3.220e9, "direct": 11.17e9}
 
 
 def parse_args():
