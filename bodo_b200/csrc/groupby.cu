@@ -604,6 +604,138 @@ __global__ void __launch_bounds__(SPG_PTHREADS, SPG_PCTAS) spg_partition_kernel(
     }
 }
 
+// K1 (TMA variant): the tile's key and value slabs are fetched with cp.async.bulk (TMA, SASS UBLKCP) into a
+// double-buffered shared-memory staging area while the previous tile is being sorted, completion is signalled on an
+// mbarrier (expect_tx / complete_tx), so no warp ever stalls on an HBM load and no row lives in registers across a
+// barrier.  Everything after the load (hash, shared-memory histogram, run reservation, staging, coalesced 16-byte
+// copy-out) is the algorithm of spg_partition_kernel.
+constexpr int SPG_TTHREADS = 512;  // threads per CTA of the TMA variant (4 rows per thread per tile), 2 CTAs per SM
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool HAS_SUM, bool HAS_CNT>
+__global__ void __launch_bounds__(SPG_TTHREADS, 2) spg_partition_tma_kernel(const __grid_constant__ SpgArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    long long* raw_k = (long long*)smem_raw;                                   // [2][SPG_TILE] keys
+    long long* raw_v = raw_k + 2 * SPG_TILE;                                   // [2][SPG_TILE] values
+    longlong2* stage = (longlong2*)(raw_v + 2 * SPG_TILE);                     // SPG_TILE x 16
+    unsigned long long* gbase = (unsigned long long*)(stage + SPG_TILE);      // SPG_MAX_OWNERS x 8
+    uint64_t* mbar = (uint64_t*)(gbase + SPG_MAX_OWNERS);                      // 2 mbarriers
+    unsigned int* hist = (unsigned int*)(mbar + 2);                            // SPG_MAX_OWNERS
+    unsigned int* lbase = hist + SPG_MAX_OWNERS;                               // SPG_MAX_OWNERS + 1
+    unsigned char* stage_owner = (unsigned char*)(lbase + SPG_MAX_OWNERS + 4);  // SPG_TILE
+    const int G = a.n_owners, tid = threadIdx.x;
+    constexpr int ROWS = SPG_TILE / SPG_TTHREADS;
+    const int64_t n_tiles = (a.n_rows + SPG_TILE - 1) / SPG_TILE;
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int j = tid; j < G; j += SPG_TTHREADS) hist[j] = 0;
+    __syncthreads();
+    // full tiles come in through TMA; a trailing partial tile is loaded with ordinary loads
+    auto issue = [&](int64_t t, int b) {
+        const int64_t r0 = t * SPG_TILE;
+        if (r0 + SPG_TILE <= a.n_rows) {
+            if (tid == 0) {
+                mbar_expect_tx(&mbar[b], (HAS_SUM ? 2u : 1u) * SPG_TILE * 8u);
+                tma_load_1d(raw_k + b * SPG_TILE, a.keys + r0, SPG_TILE * 8u, &mbar[b]);
+                if (HAS_SUM) tma_load_1d(raw_v + b * SPG_TILE, a.vals + r0, SPG_TILE * 8u, &mbar[b]);
+            }
+        }
+    };
+    uint32_t phase[2] = {0, 0};
+    int64_t t = blockIdx.x;
+    int b = 0;
+    if (t < n_tiles) issue(t, 0);
+    for (; t < n_tiles; t += gridDim.x, b ^= 1) {
+        const int64_t r0 = t * SPG_TILE;
+        const int64_t tn = t + gridDim.x;
+        if (tn < n_tiles) issue(tn, b ^ 1);  // prefetch the next tile of this CTA while this one is sorted
+        const bool full = r0 + SPG_TILE <= a.n_rows;
+        long long* kb = raw_k + b * SPG_TILE;
+        long long* vb = raw_v + b * SPG_TILE;
+        if (full) {
+            while (!mbar_try_wait(&mbar[b], phase[b])) {}
+            phase[b] ^= 1;
+        } else {
+            for (int j = tid; j < SPG_TILE; j += SPG_TTHREADS) {
+                int64_t i = r0 + j;
+                kb[j] = i < a.n_rows ? a.keys[i] : 0;
+                vb[j] = (HAS_SUM && i < a.n_rows) ? a.vals[i] : 0;
+            }
+            __syncthreads();
+        }
+        int o[ROWS];
+        unsigned int rk[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const int j = r * SPG_TTHREADS + tid;
+            o[r] = -1;
+            if (r0 + j >= a.n_rows) continue;
+            const long long k = kb[j];
+            if (k == EMPTY_KEY) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, k, HAS_SUM ? (unsigned long long)vb[j] : 0ull, 1ull); continue; }
+            o[r] = (int)spg_owner(spg_hash(k), G);
+            rk[r] = atomicAdd(&hist[o[r]], 1u);
+        }
+        __syncthreads();
+        // reserve one run per owner: the global atomic's round trip (~1 us) is kept in a register and only waited for
+        // after the staging pass, which needs the local prefix sums but not the global run start
+        unsigned long long my_gbase = 0;
+        if (tid >= SPG_TTHREADS - G) { int ow = tid - (SPG_TTHREADS - G); unsigned int cnt = hist[ow]; if (cnt) my_gbase = atomicAdd(&a.bucket_cnt[ow], (unsigned long long)cnt); }
+        if (tid < 32) {
+            unsigned int carry = 0;
+            for (int base = 0; base < G; base += 32) {
+                int j = base + tid;
+                unsigned int x = j < G ? hist[j] : 0u, inc = x;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { unsigned int y = __shfl_up_sync(0xffffffffu, inc, d); if (tid >= d) inc += y; }
+                if (j < G) lbase[j] = carry + inc - x;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (tid == 0) lbase[G] = carry;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            if (o[r] < 0) continue;
+            const int j = r * SPG_TTHREADS + tid;
+            unsigned int p = lbase[o[r]] + rk[r];
+            stage[p] = make_longlong2(kb[j], HAS_SUM ? vb[j] : 0);
+            stage_owner[p] = (unsigned char)o[r];
+        }
+        if (tid >= SPG_TTHREADS - G) gbase[tid - (SPG_TTHREADS - G)] = my_gbase;
+        __syncthreads();  // raw buffer b is free from here on (the next TMA into it is issued one iteration later)
+        const unsigned int n_tile = lbase[G];
+        for (unsigned int p = tid; p < n_tile; p += SPG_TTHREADS) {
+            unsigned int ow = stage_owner[p];
+            unsigned long long off = gbase[ow] + (p - lbase[ow]);
+            longlong2 row = stage[p];
+            if (off < (unsigned long long)a.bucket_cap) a.bucket[(size_t)ow * a.bucket_cap + off] = row;
+            else spg_direct_apply<HAS_SUM, HAS_CNT>(a, row.x, (unsigned long long)row.y, 1ull);
+        }
+        for (int j = tid; j < G; j += SPG_TTHREADS) hist[j] = 0;
+        __syncthreads();
+    }
+}
+
 // K2: one CTA per owner aggregates its bucket in shared memory, then flushes into the global table.
 template <bool HAS_SUM, bool HAS_CNT>
 __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __grid_constant__ SpgArgs a) {
@@ -929,12 +1061,19 @@ class GroupbyState {
                              (const void*)spg_partition_kernel<false, true>};
         for (auto f : pf)
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_part_smem()) != cudaSuccess) { cudaGetLastError(); return false; }
+        const void* tf[3] = {(const void*)spg_partition_tma_kernel<true, true>, (const void*)spg_partition_tma_kernel<true, false>,
+                             (const void*)spg_partition_tma_kernel<false, true>};
+        for (auto f : tf)
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_tma_smem()) != cudaSuccess) { cudaGetLastError(); return false; }
+        { const char* e2 = getenv("B200_SPG_TMA"); spg_use_tma = !(e2 && e2[0] == '0'); }
         spg_owners = sms;  // one owner (bucket + shared table) per SM
         d_bucket_cnt.alloc((size_t)spg_owners * 8);
         spg_state = 1;
         return true;
     }
 
+    bool spg_use_tma = true;
+    static size_t spg_tma_smem() { return (size_t)SPG_TILE * (32 + 16 + 1) + SPG_MAX_OWNERS * 8 + 16 + (2 * SPG_MAX_OWNERS + 4) * 4 + 256; }
     static size_t spg_part_smem() { return (size_t)SPG_TILE * 17 + SPG_MAX_OWNERS * 8 + (2 * SPG_MAX_OWNERS + 4) * 4 + 64; }
     // groups the shared-memory tables of all owners can hold together (7/8 of the slots, see occ_limit)
     int64_t spg_group_capacity() const { return (int64_t)spg_owners * (spg_ns - spg_ns / 8); }
@@ -1019,14 +1158,19 @@ class GroupbyState {
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (profiling) { B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1)); B200_CUDA(cudaEventRecord(ev0, stream)); }
             int g1 = (int)std::min<int64_t>((int64_t)sms * SPG_PCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
+            const bool tma = spg_use_tma && (((uintptr_t)a.keys & 15) == 0) && (a.vals == nullptr || ((uintptr_t)a.vals & 15) == 0);
+            int g2 = (int)std::min<int64_t>((int64_t)sms * 2, (rows + SPG_TILE - 1) / SPG_TILE);
             if (sum_j >= 0 && cnt_j >= 0) {
-                spg_partition_kernel<true, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
+                if (tma) spg_partition_tma_kernel<true, true><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
+                else spg_partition_kernel<true, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
                 spg_aggregate_kernel<true, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
             } else if (sum_j >= 0) {
-                spg_partition_kernel<true, false><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
+                if (tma) spg_partition_tma_kernel<true, false><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
+                else spg_partition_kernel<true, false><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
                 spg_aggregate_kernel<true, false><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
             } else {
-                spg_partition_kernel<false, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
+                if (tma) spg_partition_tma_kernel<false, true><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
+                else spg_partition_kernel<false, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
                 spg_aggregate_kernel<false, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
             }
             B200_CUDA(cudaGetLastError());
