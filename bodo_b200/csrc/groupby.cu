@@ -522,8 +522,8 @@ __device__ __forceinline__ void spg_direct_apply(const SpgArgs& a, long long key
         sl = find_or_insert(a.tkeys, a.cap, key, a.counters, a.group_limit);
         if (sl == ~0ull) { spg_retry_row<HAS_SUM, HAS_CNT>(a, key, sum, cnt); return; }
     }
-    if (HAS_SUM) atomicAdd(a.acc_sum + sl, sum);
-    if (HAS_CNT) atomicAdd(a.acc_cnt + sl, cnt);
+    if (HAS_SUM && sum) atomicAdd(a.acc_sum + sl, sum);
+    if (HAS_CNT && cnt) atomicAdd(a.acc_cnt + sl, cnt);
 }
 
 // K1: partition rows into owner buckets. grid = persistent (2 CTAs / SM), tiles are taken grid-stride.
@@ -609,7 +609,9 @@ __global__ void __launch_bounds__(SPG_PTHREADS, SPG_PCTAS) spg_partition_kernel(
 // mbarrier (expect_tx / complete_tx), so no warp ever stalls on an HBM load and no row lives in registers across a
 // barrier.  Everything after the load (hash, shared-memory histogram, run reservation, staging, coalesced 16-byte
 // copy-out) is the algorithm of spg_partition_kernel.
-constexpr int SPG_TTHREADS = 512;  // threads per CTA of the TMA variant (4 rows per thread per tile), 2 CTAs per SM
+constexpr int SPG_TTHREADS = 512;  // threads per CTA of the TMA variant (4 rows per thread per tile)
+constexpr int SPG_TBUFS = 1;       // raw tile buffers per CTA (1: next tile streams in during copy-out; 2: full double buffering)
+constexpr int SPG_TCTAS = 3;       // CTAs per SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -630,11 +632,11 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
 }
 
 template <bool HAS_SUM, bool HAS_CNT>
-__global__ void __launch_bounds__(SPG_TTHREADS, 2) spg_partition_tma_kernel(const __grid_constant__ SpgArgs a) {
+__global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    long long* raw_k = (long long*)smem_raw;                                   // [2][SPG_TILE] keys
-    long long* raw_v = raw_k + 2 * SPG_TILE;                                   // [2][SPG_TILE] values
-    longlong2* stage = (longlong2*)(raw_v + 2 * SPG_TILE);                     // SPG_TILE x 16
+    long long* raw_k = (long long*)smem_raw;                                   // [NB][SPG_TILE] keys
+    long long* raw_v = raw_k + SPG_TBUFS * SPG_TILE;                           // [NB][SPG_TILE] values
+    longlong2* stage = (longlong2*)(raw_v + SPG_TBUFS * SPG_TILE);             // SPG_TILE x 16
     unsigned long long* gbase = (unsigned long long*)(stage + SPG_TILE);      // SPG_MAX_OWNERS x 8
     uint64_t* mbar = (uint64_t*)(gbase + SPG_MAX_OWNERS);                      // 2 mbarriers
     unsigned int* hist = (unsigned int*)(mbar + 2);                            // SPG_MAX_OWNERS
@@ -665,10 +667,10 @@ __global__ void __launch_bounds__(SPG_TTHREADS, 2) spg_partition_tma_kernel(cons
     int64_t t = blockIdx.x;
     int b = 0;
     if (t < n_tiles) issue(t, 0);
-    for (; t < n_tiles; t += gridDim.x, b ^= 1) {
+    for (; t < n_tiles; t += gridDim.x, b ^= (SPG_TBUFS - 1)) {
         const int64_t r0 = t * SPG_TILE;
         const int64_t tn = t + gridDim.x;
-        if (tn < n_tiles) issue(tn, b ^ 1);  // prefetch the next tile of this CTA while this one is sorted
+        if (SPG_TBUFS == 2 && tn < n_tiles) issue(tn, b ^ 1);  // prefetch the next tile of this CTA while this one is sorted
         const bool full = r0 + SPG_TILE <= a.n_rows;
         long long* kb = raw_k + b * SPG_TILE;
         long long* vb = raw_v + b * SPG_TILE;
@@ -722,7 +724,8 @@ __global__ void __launch_bounds__(SPG_TTHREADS, 2) spg_partition_tma_kernel(cons
             stage_owner[p] = (unsigned char)o[r];
         }
         if (tid >= SPG_TTHREADS - G) gbase[tid - (SPG_TTHREADS - G)] = my_gbase;
-        __syncthreads();  // raw buffer b is free from here on (the next TMA into it is issued one iteration later)
+        __syncthreads();  // raw buffer b is free from here on
+        if (SPG_TBUFS == 1 && tn < n_tiles) issue(tn, 0);  // single buffer: the next tile streams in during the copy-out
         const unsigned int n_tile = lbase[G];
         for (unsigned int p = tid; p < n_tile; p += SPG_TTHREADS) {
             unsigned int ow = stage_owner[p];
@@ -742,15 +745,21 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NS = a.ns, tid = threadIdx.x, me = blockIdx.x;
     long long* skeys = (long long*)smem_raw;      // NS x 8
+    // 16 bytes per slot: key, low 32 bits of the sum, count.  The high word of an addition (value bits 32..63 plus the
+    // carry out of the low word) is almost always zero for small |values| (hi = 0xffffffff and carry = 1 cancel for
+    // small negative ones); when it is not, it is added straight to the global table, which keeps SUM exact mod 2^64.
     unsigned int* slo = (unsigned int*)(skeys + NS);  // NS x 4
-    unsigned int* shi = slo + NS;
-    unsigned int* scnt = shi + NS;
+    unsigned int* scnt = slo + NS;
     unsigned int* misc = scnt + NS;  // [0] occupied slots
-    for (int s = tid; s < NS; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0; shi[s] = 0; scnt[s] = 0; }
+    // the low word starts at 2^31 (bias) so that sums of small positive AND negative values stay away from the 32-bit
+    // wrap-around points: without it every zero crossing of a running sum would produce a high-word event
+    for (int s = tid; s < NS; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0x80000000u; scnt[s] = 0; }
     if (tid == 0) misc[0] = 0;
     __syncthreads();
     const unsigned int occ_limit = (unsigned int)(NS - NS / 8);  // keep 1/8 of the slots free so probing stays short
 
+    // NOTE (measured, r01): forcing the warp to reconverge (__syncwarp) between the probe loop and the atomics makes this
+    // kernel 25 % SLOWER — lanes that leave the loop early overlap their atomics with the other lanes' probes.
     auto upsert = [&](long long key, long long val) {
         unsigned int s = spg_slot(spg_hash(key), NS);
         bool done = false;
@@ -772,7 +781,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
             unsigned int lo = (unsigned int)(unsigned long long)val, hi = (unsigned int)((unsigned long long)val >> 32);
             unsigned int old = atomicAdd(&slo[s], lo);
             hi += (old + lo < old) ? 1u : 0u;  // carry of this very addition
-            if (hi) atomicAdd(&shi[s], hi);
+            if (hi) spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, (unsigned long long)hi << 32, 0ull);
         }
         if (HAS_CNT) atomicAdd(&scnt[s], 1u);
     };
@@ -797,7 +806,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     for (int s = tid; s < NS; s += SPG_THREADS) {
         long long key = skeys[s];
         if (key == EMPTY_KEY) continue;
-        unsigned long long sum = (unsigned long long)slo[s] | ((unsigned long long)shi[s] << 32);
+        unsigned long long sum = (unsigned long long)slo[s] - 0x80000000ull;  // remove the bias (wraps mod 2^64)
         spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, sum, (unsigned long long)scnt[s]);
     }
 }
@@ -1051,8 +1060,8 @@ class GroupbyState {
         int max_smem = 0;
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
         if (sms > SPG_MAX_OWNERS - 1 || max_smem < 64 * 1024) return false;
-        spg_ns = (int)(((size_t)max_smem - 64) / 20) & ~1;
-        spg_smem = (size_t)spg_ns * 20 + 16;
+        spg_ns = (int)(((size_t)max_smem - 64) / 16) & ~1;
+        spg_smem = (size_t)spg_ns * 16 + 16;
         const void* fns[3] = {(const void*)spg_aggregate_kernel<true, true>, (const void*)spg_aggregate_kernel<true, false>,
                               (const void*)spg_aggregate_kernel<false, true>};
         for (auto f : fns)
@@ -1073,7 +1082,7 @@ class GroupbyState {
     }
 
     bool spg_use_tma = true;
-    static size_t spg_tma_smem() { return (size_t)SPG_TILE * (32 + 16 + 1) + SPG_MAX_OWNERS * 8 + 16 + (2 * SPG_MAX_OWNERS + 4) * 4 + 256; }
+    static size_t spg_tma_smem() { return (size_t)SPG_TILE * (16 * SPG_TBUFS + 16 + 1) + SPG_MAX_OWNERS * 8 + 16 + (2 * SPG_MAX_OWNERS + 4) * 4 + 256; }
     static size_t spg_part_smem() { return (size_t)SPG_TILE * 17 + SPG_MAX_OWNERS * 8 + (2 * SPG_MAX_OWNERS + 4) * 4 + 64; }
     // groups the shared-memory tables of all owners can hold together (7/8 of the slots, see occ_limit)
     int64_t spg_group_capacity() const { return (int64_t)spg_owners * (spg_ns - spg_ns / 8); }
@@ -1159,7 +1168,7 @@ class GroupbyState {
             if (profiling) { B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1)); B200_CUDA(cudaEventRecord(ev0, stream)); }
             int g1 = (int)std::min<int64_t>((int64_t)sms * SPG_PCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
             const bool tma = spg_use_tma && (((uintptr_t)a.keys & 15) == 0) && (a.vals == nullptr || ((uintptr_t)a.vals & 15) == 0);
-            int g2 = (int)std::min<int64_t>((int64_t)sms * 2, (rows + SPG_TILE - 1) / SPG_TILE);
+            int g2 = (int)std::min<int64_t>((int64_t)sms * SPG_TCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
             if (sum_j >= 0 && cnt_j >= 0) {
                 if (tma) spg_partition_tma_kernel<true, true><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
                 else spg_partition_kernel<true, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
