@@ -811,6 +811,105 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     }
 }
 
+// ---- low-cardinality kernel (LC): every CTA keeps a private shared-memory table of ALL groups ----------------
+// Used when the (estimated) number of groups fits one CTA's table (<= LC_SLOTS / 2), e.g. BASELINE.json configs[0]
+// (20 M rows, 30 groups) where every row of a warp hits one of a handful of hot keys.  Rows are pre-aggregated inside
+// the warp when the whole warp holds ONE key (hot key / clustered input): the warp's SUM is formed with four
+// __reduce_add_sync (REDUX) over 16-bit limbs (exact: 32 lanes x 65535 < 2^32 per limb, limbs recombined mod 2^64),
+// its COUNT is popc(active), and one lane touches the shared table; otherwise each lane updates the CTA-private table
+// (CAS-probe + native 32-bit atomics with carry).  One pass over the input: 16 B/row of HBM traffic, no global atomics
+// until the final flush.
+constexpr int LC_THREADS = 512;
+constexpr int LC_SLOTS = 4096;  // per-CTA table slots (20 B each = 80 KB); groups beyond LC_SLOTS / 2 take the direct path
+
+template <bool HAS_SUM, bool HAS_CNT>
+__global__ void __launch_bounds__(LC_THREADS, 2) groupby_lowcard_kernel(const __grid_constant__ SpgArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    long long* lkeys = (long long*)smem_raw;                 // LC_SLOTS x 8
+    unsigned int* llo = (unsigned int*)(lkeys + LC_SLOTS);  // low / high words of the sum, count
+    unsigned int* lhi = llo + LC_SLOTS;
+    unsigned int* lcnt = lhi + LC_SLOTS;
+    unsigned int* misc = lcnt + LC_SLOTS;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int s = tid; s < LC_SLOTS; s += LC_THREADS) { lkeys[s] = EMPTY_KEY; llo[s] = 0; lhi[s] = 0; lcnt[s] = 0; }
+    if (tid == 0) misc[0] = 0;
+    __syncthreads();
+
+    auto leader_upsert = [&](long long key, unsigned long long sum, unsigned int cnt) {
+        unsigned int s = (unsigned int)(spg_hash(key) >> 32) & (LC_SLOTS - 1);
+        bool done = false;
+        for (int probes = 0; probes < LC_SLOTS; probes++) {
+            long long kk = lkeys[s];
+            if (kk == EMPTY_KEY) {
+                unsigned int t = atomicAdd(&misc[0], 1u);
+                if (t >= LC_SLOTS / 2) { atomicSub(&misc[0], 1u); break; }
+                long long prev = (long long)atomicCAS((unsigned long long*)&lkeys[s], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                if (prev == EMPTY_KEY) { done = true; break; }
+                atomicSub(&misc[0], 1u);
+                kk = prev;
+            }
+            if (kk == key) { done = true; break; }
+            s = (s + 1) & (LC_SLOTS - 1);
+        }
+        if (!done) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, sum, (unsigned long long)cnt); return; }
+        if (HAS_SUM) {
+            unsigned int lo = (unsigned int)sum, hi = (unsigned int)(sum >> 32);
+            unsigned int old = atomicAdd(&llo[s], lo);
+            hi += (old + lo < old) ? 1u : 0u;
+            if (hi) atomicAdd(&lhi[s], hi);
+        }
+        if (HAS_CNT) atomicAdd(&lcnt[s], cnt);
+    };
+
+    // warp-uniform trip count (bounds checked per row): the warp collectives below need converged warps
+    const int64_t stride = (int64_t)gridDim.x * LC_THREADS * 2;
+    const int64_t n_round = (a.n_rows + 63) & ~63ll;
+    for (int64_t i = ((int64_t)blockIdx.x * LC_THREADS + tid) * 2; i < n_round; i += stride) {
+        long long k[2] = {0, 0}, v[2] = {0, 0};
+        bool ok[2] = {i < a.n_rows, i + 1 < a.n_rows};
+        if (ok[1]) {
+            longlong2 kk = __ldcs(reinterpret_cast<const longlong2*>(a.keys + i));
+            k[0] = kk.x; k[1] = kk.y;
+            if (HAS_SUM) { longlong2 vv = __ldcs(reinterpret_cast<const longlong2*>(a.vals + i)); v[0] = vv.x; v[1] = vv.y; }
+        } else if (ok[0]) {
+            k[0] = a.keys[i];
+            if (HAS_SUM) v[0] = a.vals[i];
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (ok[r] && k[r] == EMPTY_KEY) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, k[r], (unsigned long long)v[r], 1ull); ok[r] = false; }
+            const unsigned act = __ballot_sync(0xffffffffu, ok[r]);
+            if (!ok[r]) continue;
+            // warp-uniform shortcut (one hot key, sorted / clustered input): reduce the whole warp with REDUX and let one
+            // lane update the table.  Otherwise every lane updates the CTA table itself: for >= ~30 distinct keys per warp
+            // a __match_any_sync based pre-aggregation was measured 3-5x slower (it serialises over the distinct keys).
+            const long long k0 = __shfl_sync(act, k[r], __ffs(act) - 1);
+            const bool uniform = __all_sync(act, k[r] == k0) && act != (1u << (__ffs(act) - 1));
+            if (uniform) {
+                unsigned long long sum = 0;
+                if (HAS_SUM) {
+                    const unsigned long long u = (unsigned long long)v[r];
+                    const unsigned int l0 = __reduce_add_sync(act, (unsigned int)(u & 0xffffu));
+                    const unsigned int l1 = __reduce_add_sync(act, (unsigned int)((u >> 16) & 0xffffu));
+                    const unsigned int l2 = __reduce_add_sync(act, (unsigned int)((u >> 32) & 0xffffu));
+                    const unsigned int l3 = __reduce_add_sync(act, (unsigned int)(u >> 48));
+                    sum = (unsigned long long)l0 + ((unsigned long long)l1 << 16) + ((unsigned long long)l2 << 32) + ((unsigned long long)l3 << 48);
+                }
+                if (lane == __ffs(act) - 1) leader_upsert(k0, sum, (unsigned int)__popc(act));
+            } else {
+                leader_upsert(k[r], (unsigned long long)v[r], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < LC_SLOTS; s += LC_THREADS) {
+        long long key = lkeys[s];
+        if (key == EMPTY_KEY) continue;
+        unsigned long long sum = (unsigned long long)llo[s] | ((unsigned long long)lhi[s] << 32);
+        spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, sum, (unsigned long long)lcnt[s]);
+    }
+}
+
 // ================================================================================================
 // Host side
 // ================================================================================================
@@ -1049,7 +1148,7 @@ class GroupbyState {
     int spg_owners = 0, spg_ns = 0;
     size_t spg_smem = 0;
     int spg_state = -1;  // -1 not probed, 0 unavailable/disabled, 1 ready
-    int64_t spg_launches = 0, spg_retry_rows = 0;
+    int64_t spg_launches = 0, spg_retry_rows = 0, lc_launches = 0;
     int64_t expected_groups_hint = 0;
 
     bool spg_probe() {
@@ -1075,13 +1174,18 @@ class GroupbyState {
         for (auto f : tf)
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_tma_smem()) != cudaSuccess) { cudaGetLastError(); return false; }
         { const char* e2 = getenv("B200_SPG_TMA"); spg_use_tma = !(e2 && e2[0] == '0'); }
+        const void* lf[3] = {(const void*)groupby_lowcard_kernel<true, true>, (const void*)groupby_lowcard_kernel<true, false>,
+                             (const void*)groupby_lowcard_kernel<false, true>};
+        for (auto f : lf)
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)LC_SLOTS * 20 + 64)) != cudaSuccess) { cudaGetLastError(); return false; }
+        { const char* e3 = getenv("B200_LC"); lc_enabled = !(e3 && e3[0] == '0'); }
         spg_owners = sms;  // one owner (bucket + shared table) per SM
         d_bucket_cnt.alloc((size_t)spg_owners * 8);
         spg_state = 1;
         return true;
     }
 
-    bool spg_use_tma = true;
+    bool spg_use_tma = true, lc_enabled = true;
     static size_t spg_tma_smem() { return (size_t)SPG_TILE * (16 * SPG_TBUFS + 16 + 1) + SPG_MAX_OWNERS * 8 + 16 + (2 * SPG_MAX_OWNERS + 4) * 4 + 256; }
     static size_t spg_part_smem() { return (size_t)SPG_TILE * 17 + SPG_MAX_OWNERS * 8 + (2 * SPG_MAX_OWNERS + 4) * 4 + 64; }
     // groups the shared-memory tables of all owners can hold together (7/8 of the slots, see occ_limit)
@@ -1131,7 +1235,7 @@ class GroupbyState {
         }
     }
 
-    void consume_spg(const long long* keys, const long long* vals, int64_t n, int sum_j, int cnt_j) {
+    void consume_spg(const long long* keys, const long long* vals, int64_t n, int sum_j, int cnt_j, bool lowcard = false) {
         if (!h_spg) {
             h_spg = (long long*)pinned_acquire(16 * sizeof(long long));
             for (int b = 0; b < 2; b++) B200_CUDA(cudaEventCreateWithFlags(&spg_ev[b], cudaEventDisableTiming));
@@ -1166,21 +1270,30 @@ class GroupbyState {
             a.sum_first = (sum_j >= 0 && cnt_j >= 0 && sum_j < cnt_j) ? 1 : 0; a.ns = spg_ns;
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (profiling) { B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1)); B200_CUDA(cudaEventRecord(ev0, stream)); }
-            int g1 = (int)std::min<int64_t>((int64_t)sms * SPG_PCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
-            const bool tma = spg_use_tma && (((uintptr_t)a.keys & 15) == 0) && (a.vals == nullptr || ((uintptr_t)a.vals & 15) == 0);
-            int g2 = (int)std::min<int64_t>((int64_t)sms * SPG_TCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
-            if (sum_j >= 0 && cnt_j >= 0) {
-                if (tma) spg_partition_tma_kernel<true, true><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
-                else spg_partition_kernel<true, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
-                spg_aggregate_kernel<true, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
-            } else if (sum_j >= 0) {
-                if (tma) spg_partition_tma_kernel<true, false><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
-                else spg_partition_kernel<true, false><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
-                spg_aggregate_kernel<true, false><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+            if (lowcard) {
+                int gl = (int)std::min<int64_t>((int64_t)sms * 2, (rows + LC_THREADS * 2 - 1) / (LC_THREADS * 2));
+                size_t lsm = (size_t)LC_SLOTS * 20 + 64;
+                if (sum_j >= 0 && cnt_j >= 0) groupby_lowcard_kernel<true, true><<<gl, LC_THREADS, lsm, stream>>>(a);
+                else if (sum_j >= 0) groupby_lowcard_kernel<true, false><<<gl, LC_THREADS, lsm, stream>>>(a);
+                else groupby_lowcard_kernel<false, true><<<gl, LC_THREADS, lsm, stream>>>(a);
+                lc_launches++;
             } else {
-                if (tma) spg_partition_tma_kernel<false, true><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
-                else spg_partition_kernel<false, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
-                spg_aggregate_kernel<false, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+                int g1 = (int)std::min<int64_t>((int64_t)sms * SPG_PCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
+                const bool tma = spg_use_tma && (((uintptr_t)a.keys & 15) == 0) && (a.vals == nullptr || ((uintptr_t)a.vals & 15) == 0);
+                int g2 = (int)std::min<int64_t>((int64_t)sms * SPG_TCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
+                if (sum_j >= 0 && cnt_j >= 0) {
+                    if (tma) spg_partition_tma_kernel<true, true><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
+                    else spg_partition_kernel<true, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
+                    spg_aggregate_kernel<true, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+                } else if (sum_j >= 0) {
+                    if (tma) spg_partition_tma_kernel<true, false><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
+                    else spg_partition_kernel<true, false><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
+                    spg_aggregate_kernel<true, false><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+                } else {
+                    if (tma) spg_partition_tma_kernel<false, true><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
+                    else spg_partition_kernel<false, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
+                    spg_aggregate_kernel<false, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+                }
             }
             B200_CUDA(cudaGetLastError());
             if (ev0) { B200_CUDA(cudaEventRecord(ev1, stream)); prof_events.emplace_back(ev0, ev1); }
@@ -1225,12 +1338,12 @@ class GroupbyState {
                 est = n_groups;
                 if (prefix == n) return;
                 for (int c = 0; c < n_cols; c++) if (data[c]) d2[c] = (const char*)data[c] + prefix * ctype_size(c_types[c]);
-                if (est <= spg_group_capacity()) consume_spg((const long long*)d2[0], vcol >= 0 ? (const long long*)d2[vcol] : nullptr, n - prefix, sum_j, cnt_j);
+                if (est <= spg_group_capacity()) consume_spg((const long long*)d2[0], vcol >= 0 ? (const long long*)d2[vcol] : nullptr, n - prefix, sum_j, cnt_j, lc_enabled && est <= LC_SLOTS / 4);
                 else consume_direct(d2, v2, n - prefix, fast, sum_j, cnt_j, vcol, false);
                 return;
             }
             if (force || est <= spg_group_capacity()) {
-                consume_spg((const long long*)data[0], vcol >= 0 ? (const long long*)data[vcol] : nullptr, n, sum_j, cnt_j);
+                consume_spg((const long long*)data[0], vcol >= 0 ? (const long long*)data[vcol] : nullptr, n, sum_j, cnt_j, lc_enabled && est > 0 && est <= LC_SLOTS / 4);
                 return;
             }
         }
@@ -1590,6 +1703,7 @@ int64_t b200_groupby_get_metric(void* state, int32_t which) {
         case 7: return s->consume_launches;
         case 8: return s->spg_launches;
         case 9: return s->spg_retry_rows;
+        case 10: return s->lc_launches;
         case 100: s->profiling = true; return 0;
         default: return -1;
     }

@@ -165,3 +165,28 @@ def test_sm_partitioned_path_vs_oracle(gpu_lib, oracle, n_groups, hint, funcs):
     assert_frames_equal(positional(got), exp)
     if n_groups <= 1_000_000:
         assert used_spg >= 1, "the SM-partitioned kernel was expected to run for this shape"
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("n_groups", [1, 30, 700, 3000])
+def test_low_cardinality_warp_aggregated_path_exact(gpu_lib, oracle, n_groups):
+    # few hot keys -> the low-cardinality kernel (match_any + REDUX limb sums + leader upsert); extreme int64 values
+    # exercise the 16-bit limb recombination and the carry into the high word: SUM must be exact mod 2^64
+    from bodo_b200.streaming.groupby import (delete_groupby_state, get_metric, groupby_build_consume_batch,
+                                             groupby_produce_output_batch, init_groupby_state)
+    from tests.helpers import table_to_device
+    rng = np.random.default_rng(n_groups)
+    n = 1_300_003
+    k = rng.integers(0, n_groups, n).astype(np.int64) * 7919 - 5
+    v = rng.integers(-(2**62), 2**62, n).astype(np.int64)
+    v[::3] = rng.integers(-500, 500, len(v[::3]))
+    t = Table.from_pandas(pd.DataFrame({"k": k, "v": v}))
+    st = init_groupby_state(-1, (0,), ("sum", "count"), (0, 1, 2), (1, 1), expected_groups=n_groups, output_batch_size=1 << 30)
+    groupby_build_consume_batch(st, table_to_device(t), True, True)
+    lc = get_metric(st, 10)
+    out, last = groupby_produce_output_batch(st, True)
+    got = out.to_pandas()
+    delete_groupby_state(st)
+    assert_frames_equal(positional(got), oracle_groupby_frame(oracle, t, 0, ["sum", "count"], [1, 1]))
+    if n_groups <= 1024:
+        assert lc >= 1, "the low-cardinality kernel was expected to run"
