@@ -820,10 +820,12 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
 // (CAS-probe + native 32-bit atomics with carry).  One pass over the input: 16 B/row of HBM traffic, no global atomics
 // until the final flush.
 constexpr int LC_THREADS = 512;
-constexpr int LC_SLOTS = 4096;  // per-CTA table slots (20 B each = 80 KB); groups beyond LC_SLOTS / 2 take the direct path
+// per-CTA table slots (20 B each); groups beyond LC_SLOTS / 2 take the direct path.  Two instantiations: 1024 slots
+// (3 CTAs = 1536 threads per SM, for <= 256 expected groups) and 4096 slots (2 CTAs per SM, <= 1024 expected groups).
+constexpr int LC_SLOTS_BIG = 4096, LC_SLOTS_SMALL = 1024;
 
-template <bool HAS_SUM, bool HAS_CNT>
-__global__ void __launch_bounds__(LC_THREADS, 2) groupby_lowcard_kernel(const __grid_constant__ SpgArgs a) {
+template <bool HAS_SUM, bool HAS_CNT, int LC_SLOTS, int MIN_CTAS>
+__global__ void __launch_bounds__(LC_THREADS, MIN_CTAS) groupby_lowcard_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     long long* lkeys = (long long*)smem_raw;                 // LC_SLOTS x 8
     unsigned int* llo = (unsigned int*)(lkeys + LC_SLOTS);  // low / high words of the sum, count
@@ -1174,10 +1176,10 @@ class GroupbyState {
         for (auto f : tf)
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_tma_smem()) != cudaSuccess) { cudaGetLastError(); return false; }
         { const char* e2 = getenv("B200_SPG_TMA"); spg_use_tma = !(e2 && e2[0] == '0'); }
-        const void* lf[3] = {(const void*)groupby_lowcard_kernel<true, true>, (const void*)groupby_lowcard_kernel<true, false>,
-                             (const void*)groupby_lowcard_kernel<false, true>};
+        const void* lf[3] = {(const void*)groupby_lowcard_kernel<true, true, LC_SLOTS_BIG, 2>, (const void*)groupby_lowcard_kernel<true, false, LC_SLOTS_BIG, 2>,
+                             (const void*)groupby_lowcard_kernel<false, true, LC_SLOTS_BIG, 2>};
         for (auto f : lf)
-            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)LC_SLOTS * 20 + 64)) != cudaSuccess) { cudaGetLastError(); return false; }
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)LC_SLOTS_BIG * 20 + 64)) != cudaSuccess) { cudaGetLastError(); return false; }
         { const char* e3 = getenv("B200_LC"); lc_enabled = !(e3 && e3[0] == '0'); }
         spg_owners = sms;  // one owner (bucket + shared table) per SM
         d_bucket_cnt.alloc((size_t)spg_owners * 8);
@@ -1185,9 +1187,10 @@ class GroupbyState {
         return true;
     }
 
-    bool spg_use_tma = true, lc_enabled = true;
+    bool spg_use_tma = true, lc_enabled = true, lowcard_small = false;
     static size_t spg_tma_smem() { return (size_t)SPG_TILE * (16 * SPG_TBUFS + 16 + 1) + SPG_MAX_OWNERS * 8 + 16 + (2 * SPG_MAX_OWNERS + 4) * 4 + 256; }
     static size_t spg_part_smem() { return (size_t)SPG_TILE * 17 + SPG_MAX_OWNERS * 8 + (2 * SPG_MAX_OWNERS + 4) * 4 + 64; }
+    bool lc_pick(int64_t est) { lowcard_small = est <= LC_SLOTS_SMALL / 4; return lc_enabled && est <= LC_SLOTS_BIG / 4; }
     // groups the shared-memory tables of all owners can hold together (7/8 of the slots, see occ_limit)
     int64_t spg_group_capacity() const { return (int64_t)spg_owners * (spg_ns - spg_ns / 8); }
 
@@ -1271,11 +1274,18 @@ class GroupbyState {
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (profiling) { B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1)); B200_CUDA(cudaEventRecord(ev0, stream)); }
             if (lowcard) {
-                int gl = (int)std::min<int64_t>((int64_t)sms * 2, (rows + LC_THREADS * 2 - 1) / (LC_THREADS * 2));
-                size_t lsm = (size_t)LC_SLOTS * 20 + 64;
-                if (sum_j >= 0 && cnt_j >= 0) groupby_lowcard_kernel<true, true><<<gl, LC_THREADS, lsm, stream>>>(a);
-                else if (sum_j >= 0) groupby_lowcard_kernel<true, false><<<gl, LC_THREADS, lsm, stream>>>(a);
-                else groupby_lowcard_kernel<false, true><<<gl, LC_THREADS, lsm, stream>>>(a);
+                const bool small = lowcard_small;
+                int gl = (int)std::min<int64_t>((int64_t)sms * (small ? 3 : 2), (rows + LC_THREADS * 2 - 1) / (LC_THREADS * 2));
+                size_t lsm = (size_t)(small ? LC_SLOTS_SMALL : LC_SLOTS_BIG) * 20 + 64;
+                if (small) {
+                    if (sum_j >= 0 && cnt_j >= 0) groupby_lowcard_kernel<true, true, LC_SLOTS_SMALL, 3><<<gl, LC_THREADS, lsm, stream>>>(a);
+                    else if (sum_j >= 0) groupby_lowcard_kernel<true, false, LC_SLOTS_SMALL, 3><<<gl, LC_THREADS, lsm, stream>>>(a);
+                    else groupby_lowcard_kernel<false, true, LC_SLOTS_SMALL, 3><<<gl, LC_THREADS, lsm, stream>>>(a);
+                } else {
+                    if (sum_j >= 0 && cnt_j >= 0) groupby_lowcard_kernel<true, true, LC_SLOTS_BIG, 2><<<gl, LC_THREADS, lsm, stream>>>(a);
+                    else if (sum_j >= 0) groupby_lowcard_kernel<true, false, LC_SLOTS_BIG, 2><<<gl, LC_THREADS, lsm, stream>>>(a);
+                    else groupby_lowcard_kernel<false, true, LC_SLOTS_BIG, 2><<<gl, LC_THREADS, lsm, stream>>>(a);
+                }
                 lc_launches++;
             } else {
                 int g1 = (int)std::min<int64_t>((int64_t)sms * SPG_PCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
@@ -1338,12 +1348,12 @@ class GroupbyState {
                 est = n_groups;
                 if (prefix == n) return;
                 for (int c = 0; c < n_cols; c++) if (data[c]) d2[c] = (const char*)data[c] + prefix * ctype_size(c_types[c]);
-                if (est <= spg_group_capacity()) consume_spg((const long long*)d2[0], vcol >= 0 ? (const long long*)d2[vcol] : nullptr, n - prefix, sum_j, cnt_j, lc_enabled && est <= LC_SLOTS / 4);
+                if (est <= spg_group_capacity()) consume_spg((const long long*)d2[0], vcol >= 0 ? (const long long*)d2[vcol] : nullptr, n - prefix, sum_j, cnt_j, lc_pick(est));
                 else consume_direct(d2, v2, n - prefix, fast, sum_j, cnt_j, vcol, false);
                 return;
             }
             if (force || est <= spg_group_capacity()) {
-                consume_spg((const long long*)data[0], vcol >= 0 ? (const long long*)data[vcol] : nullptr, n, sum_j, cnt_j, lc_enabled && est > 0 && est <= LC_SLOTS / 4);
+                consume_spg((const long long*)data[0], vcol >= 0 ? (const long long*)data[vcol] : nullptr, n, sum_j, cnt_j, est > 0 && lc_pick(est));
                 return;
             }
         }
