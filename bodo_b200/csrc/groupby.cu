@@ -245,8 +245,9 @@ __global__ void rehash_kernel(const __grid_constant__ RehashArgs a) {
 }
 
 // ---- finalize: compact occupied slots, then evaluate output columns ----
-__global__ void compact_slots_kernel(const long long* __restrict__ tkeys, uint64_t cap, int na_present, int empty_present,
+__global__ void compact_slots_kernel(const long long* __restrict__ tkeys, uint64_t cap, const long long* counters,
                                      long long* cursor, uint64_t* slot_of_out) {
+    const bool na_present = counters[3] != 0, empty_present = counters[4] != 0;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t s0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s0 < ((cap + 2 + 31) & ~31ull); s0 += stride) {
         bool occ = false;
@@ -274,7 +275,7 @@ struct EvalArgs {
     const long long* tkeys;
     uint64_t cap;
     const uint64_t* slot_of_out;
-    int64_t n_out;
+    const long long* n_out_ptr;  // number of compacted slots (device counter written by compact_slots_kernel)
     int key_ctype;
     void* out_keys;
     uint32_t* out_key_valid;  // nullptr unless the NA-key group can exist
@@ -298,9 +299,10 @@ __device__ __forceinline__ void store_f_typed(void* p, int ct, int64_t i, double
 // groupby/_groupby_common.cpp:50-74: sum/count/size valid, min/max/mean NULL when nothing was seen).
 __global__ void eval_output_kernel(const __grid_constant__ EvalArgs a) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t n_round = (a.n_out + 31) & ~31ll;
+    const int64_t n_out = *a.n_out_ptr;
+    int64_t n_round = (n_out + 31) & ~31ll;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_round; p += stride) {
-        bool in = p < a.n_out;
+        bool in = p < n_out;
         uint64_t s = in ? a.slot_of_out[p] : 0;
         bool key_ok = true;
         if (in) {
@@ -1489,12 +1491,11 @@ class GroupbyState {
         int64_t max_out = n_groups + 2;
         d_slot_of_out.ensure((size_t)max_out * 8);
         B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 16, 0, 8, stream));
-        compact_slots_kernel<<<grid_for((int64_t)cap + 2), 256, 0, stream>>>(d_keys.as<long long>(), cap, (int)h_counters[3], (int)h_counters[4],
+        compact_slots_kernel<<<grid_for((int64_t)cap + 2), 256, 0, stream>>>(d_keys.as<long long>(), cap, d_counters.as<long long>(),
                                                                                   d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>());
         launches++;
         B200_CUDA(cudaGetLastError());
-        read_counters();
-        n_out = h_counters[2];
+        n_out = -1;  // known on the device (counters[2]); the host learns it with the next counter read-back
     }
 
     int64_t finalize() {
@@ -1503,28 +1504,28 @@ class GroupbyState {
         struct Acc3 { double& t; double t0; ~Acc3() { t += now() - t0; } } acc3{t_finalize, tf0};
         B200_CUDA(cudaSetDevice(device));
         compact();
+        const int64_t max_out = n_groups + 2;  // exact group count (+ the two special slots) from compact()'s read-back
         EvalArgs e{};
-        e.tkeys = d_keys.as<long long>(); e.cap = cap; e.slot_of_out = d_slot_of_out.as<uint64_t>(); e.n_out = n_out;
+        e.tkeys = d_keys.as<long long>(); e.cap = cap; e.slot_of_out = d_slot_of_out.as<uint64_t>(); e.n_out_ptr = d_counters.as<long long>() + 2;
         e.key_ctype = c_types[0];
-        size_t words = (size_t)((n_out + 31) / 32 + 1);
-        d_out_keys.ensure((size_t)(n_out + 32) * ctype_size(c_types[0]));
+        size_t words = (size_t)((max_out + 31) / 32 + 1);
+        d_out_keys.ensure((size_t)(max_out + 32) * ctype_size(c_types[0]));
         e.out_keys = d_out_keys.p;
         bool key_nullable = arr_types[0] == ARR_NULLABLE;
         if (key_nullable) { d_out_key_valid.ensure(words * 4); e.out_key_valid = d_out_key_valid.as<uint32_t>(); }
         e.n_ops = n_funcs;
         for (int j = 0; j < n_funcs; j++) {
             const FuncSpec& f = funcs[j];
-            d_out_data[j].ensure((size_t)(n_out + 32) * 8);
+            d_out_data[j].ensure((size_t)(max_out + 32) * 8);
             e.ops[j].kind = f.kind; e.ops[j].out_ctype = f.out_ctype; e.ops[j].a0 = d_a0[j].p;
             e.ops[j].a1 = f.has_a1 ? d_a1[j].p : nullptr; e.ops[j].out_data = d_out_data[j].p;
             if (f.out_arrtype == ARR_NULLABLE) { d_out_valid[j].ensure(words * 4); e.ops[j].out_valid = d_out_valid[j].as<uint32_t>(); }
         }
-        if (n_out > 0) {
-            eval_output_kernel<<<grid_for(n_out), 256, 0, stream>>>(e);
-            launches++;
-            B200_CUDA(cudaGetLastError());
-        }
-        B200_CUDA(cudaStreamSynchronize(stream));
+        eval_output_kernel<<<grid_for(max_out), 256, 0, stream>>>(e);
+        launches++;
+        B200_CUDA(cudaGetLastError());
+        read_counters();  // one synchronisation: the output is complete and n_out is known
+        n_out = h_counters[2];
         finalized = true;
         out_cursor = 0;
         return n_out;
@@ -1537,6 +1538,8 @@ class GroupbyState {
         B200_CUDA(cudaSetDevice(device));
         build_done = true;
         compact();
+        read_counters();
+        n_out = h_counters[2];
         d_dest_count.ensure((size_t)n_pes * 8);
         B200_CUDA(cudaMemsetAsync(d_dest_count.p, 0, (size_t)n_pes * 8, stream));
         PackArgs p = pack_args();
