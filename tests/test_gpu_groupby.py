@@ -190,3 +190,24 @@ def test_low_cardinality_warp_aggregated_path_exact(gpu_lib, oracle, n_groups):
     assert_frames_equal(positional(got), oracle_groupby_frame(oracle, t, 0, ["sum", "count"], [1, 1]))
     if n_groups <= 1024:
         assert lc >= 1, "the low-cardinality kernel was expected to run"
+
+
+@pytest.mark.timeout(300)
+def test_sm_partitioned_path_skewed_keys(gpu_lib, oracle):
+    # Zipf-like keys: a few owners receive far more rows than their bucket holds, so K1 sends the excess through the
+    # direct global path; hot keys hammer single shared-memory slots in K2.  Result must still be bit-exact.
+    from bodo_b200.streaming.groupby import (delete_groupby_state, get_metric, groupby_build_consume_batch,
+                                             groupby_produce_output_batch, init_groupby_state)
+    from tests.helpers import table_to_device
+    rng = np.random.default_rng(99)
+    n = 3_000_000
+    k = np.minimum(rng.zipf(1.2, n), 200_000).astype(np.int64) * 31 + 7
+    v = rng.integers(-(2**40), 2**40, n).astype(np.int64)
+    t = Table.from_pandas(pd.DataFrame({"k": k, "v": v}))
+    st = init_groupby_state(-1, (0,), ("sum", "count"), (0, 1, 2), (1, 1), expected_groups=100_000, output_batch_size=1 << 30)
+    groupby_build_consume_batch(st, table_to_device(t), True, True)
+    assert get_metric(st, 8) >= 1
+    out, last = groupby_produce_output_batch(st, True)
+    got = out.to_pandas()
+    delete_groupby_state(st)
+    assert_frames_equal(positional(got), oracle_groupby_frame(oracle, t, 0, ["sum", "count"], [1, 1]))
