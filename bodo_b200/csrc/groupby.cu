@@ -83,7 +83,8 @@ __device__ __forceinline__ uint64_t find_or_insert(long long* __restrict__ tkeys
     return ~0ull;
 }
 
-__device__ __forceinline__ void apply_ops(const ConsumeArgs& a, uint64_t slot, int64_t row) {
+template <typename A>
+__device__ __forceinline__ void apply_ops(const A& a, uint64_t slot, int64_t row) {
 #pragma unroll 1
     for (int j = 0; j < a.n_ops; j++) {
         const OpDesc& op = a.ops[j];
@@ -305,7 +306,7 @@ __global__ void eval_output_kernel(const __grid_constant__ EvalArgs a) {
         bool in = p < n_out;
         uint64_t s = in ? a.slot_of_out[p] : 0;
         bool key_ok = true;
-        if (in) {
+        if (in && a.tkeys) {  // single-key tables only (multi-key tables write their key columns in eval_mk_keys_kernel)
             long long key = s < a.cap ? a.tkeys[s] : (s == a.cap ? 0 : EMPTY_KEY);
             key_ok = s != a.cap;
             store_int_typed(a.out_keys, a.key_ctype, p, key);
@@ -449,6 +450,160 @@ __global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
                 case K_MAX_F64: atomicMax((unsigned long long*)a.a0[j] + slot, v0); break;
             }
             if (a.a1[j] && a.kinds[j] != K_MEAN) atomicAdd((unsigned long long*)a.a1[j] + slot, v1);
+        }
+    }
+}
+
+// ---- multi-column keys (2..4 integer key columns; SURVEY.md §8f "next" row 1, the reference's select-distinct /
+// multi-key groupby: bodo/tests/test_streaming/test_groupby.py:111-177) -----------------------------------------
+// A slot is claimed through a 64-bit tag word (hash of the key tuple, bit 63 set; 0 = empty, 1 = being written): the
+// claiming thread CASes empty -> locked, writes the key columns + NA mask of the slot, fences and publishes the tag.
+// Readers that find their own tag compare the full tuple (so the result is exact, the tag only prunes); readers that
+// find `locked` re-read the slot.  Aggregate updates are the single-key kernel's apply_ops.
+constexpr int MAX_KEYS = 4;
+constexpr unsigned long long TAG_EMPTY = 0ull, TAG_LOCKED = 1ull;
+
+struct MkArgs {
+    int nk;
+    const void* key_data[MAX_KEYS];
+    const uint8_t* key_valid[MAX_KEYS];
+    int key_ctype[MAX_KEYS];
+    int dropna;
+    int64_t n_rows;
+    const uint32_t* index_list;
+    unsigned long long* tags;
+    long long* mk[MAX_KEYS];
+    unsigned char* mkmask;  // bit j = key column j is valid (not NA) in this group's key
+    uint64_t cap;
+    long long* counters;
+    long long group_limit;
+    uint32_t* fail_list;
+    int n_ops;
+    OpDesc ops[MAX_OPS];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long mk_tag(const long long* keys, unsigned int mask, int nk) {
+    unsigned long long h = 0x9E3779B97F4A7C15ULL ^ mask;
+    for (int j = 0; j < nk; j++) h = xxh3_64_short((unsigned long long)keys[j] ^ (h * 0xD1B54A32D192ED03ULL), 8, SEED_HASH_PARTITION + j);
+    return h | 0x8000000000000000ULL;
+}
+template <typename A>
+__device__ __forceinline__ uint64_t find_or_insert_mk(const A& a, const long long* keys, unsigned int mask, unsigned long long tag) {
+    const uint64_t m = a.cap - 1;
+    uint64_t s = (tag >> 20) & m;
+    for (uint64_t probes = 0; probes <= m;) {
+        unsigned long long t = ld_acquire_u64(a.tags + s);
+        if (t == tag) {
+            bool eq = __ldcg(a.mkmask + s) == (unsigned char)mask;
+            for (int j = 0; j < a.nk && eq; j++) eq = __ldcg(a.mk[j] + s) == keys[j];
+            if (eq) return s;
+        } else if (t == TAG_EMPTY) {
+            if (a.group_limit >= 0) {
+                long long tk = atomicAdd((unsigned long long*)&a.counters[0], 1ull);
+                if (tk >= a.group_limit) { atomicAdd((unsigned long long*)&a.counters[0], (unsigned long long)-1ll); return ~0ull; }
+            }
+            unsigned long long old = atomicCAS(a.tags + s, TAG_EMPTY, TAG_LOCKED);
+            if (old == TAG_EMPTY) {
+                for (int j = 0; j < a.nk; j++) a.mk[j][s] = keys[j];
+                a.mkmask[s] = (unsigned char)mask;
+                __threadfence();
+                atomicExch(a.tags + s, tag);  // publish
+                return s;
+            }
+            if (a.group_limit >= 0) atomicAdd((unsigned long long*)&a.counters[0], (unsigned long long)-1ll);
+            continue;  // somebody else took the slot: look at it again
+        } else if (t == TAG_LOCKED) {
+            continue;  // being written: re-read
+        }
+        s = (s + 1) & m;
+        probes++;
+    }
+    return ~0ull;
+}
+
+__global__ void __launch_bounds__(256) groupby_consume_mk_kernel(const __grid_constant__ MkArgs a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_rows; i += stride) {
+        int64_t row = a.index_list ? (int64_t)a.index_list[i] : i;
+        long long keys[MAX_KEYS];
+        unsigned int mask = 0;
+        for (int j = 0; j < a.nk; j++) {
+            bool v = bit_valid(a.key_valid[j], row);
+            keys[j] = v ? (long long)load_int_as_i64(a.key_data[j], a.key_ctype[j], row) : 0;
+            mask |= v ? (1u << j) : 0u;
+        }
+        if (a.dropna && mask != (1u << a.nk) - 1u) continue;  // any NA key column drops the row (pandas dropna=True)
+        uint64_t slot = find_or_insert_mk(a, keys, mask, mk_tag(keys, mask, a.nk));
+        if (slot == ~0ull) {
+            unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
+            a.fail_list[f] = (uint32_t)row;
+            continue;
+        }
+        apply_ops(a, slot, row);
+    }
+}
+
+struct RehashMkArgs {
+    int nk;
+    const unsigned long long* old_tags; const long long* old_mk[MAX_KEYS]; const unsigned char* old_mask; uint64_t old_cap;
+    unsigned long long* tags; long long* mk[MAX_KEYS]; unsigned char* mkmask; uint64_t cap;
+    long long* counters; long long group_limit;  // group_limit < 0: no limit
+    int n_acc;
+    const unsigned long long* old_acc[2 * MAX_OPS];
+    unsigned long long* new_acc[2 * MAX_OPS];
+};
+__global__ void rehash_mk_kernel(const __grid_constant__ RehashMkArgs a) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < a.old_cap; s += stride) {
+        unsigned long long t = a.old_tags[s];
+        if (!(t >> 63)) continue;
+        long long keys[MAX_KEYS];
+        for (int j = 0; j < a.nk; j++) keys[j] = a.old_mk[j][s];
+        uint64_t ns = find_or_insert_mk(a, keys, a.old_mask[s], t);
+        for (int j = 0; j < a.n_acc; j++) a.new_acc[j][ns] = a.old_acc[j][s];
+    }
+}
+__global__ void compact_mk_kernel(const unsigned long long* __restrict__ tags, uint64_t cap, long long* cursor, uint64_t* slot_of_out) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s0 < ((cap + 31) & ~31ull); s0 += stride) {
+        bool occ = s0 < cap && (tags[s0] >> 63);
+        unsigned m = __ballot_sync(0xffffffffu, occ);
+        int lane = threadIdx.x & 31;
+        long long base = 0;
+        if (lane == 0 && m) base = (long long)atomicAdd((unsigned long long*)cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (occ) slot_of_out[base + __popc(m & ((1u << lane) - 1))] = s0;
+    }
+}
+struct EvalMkKeysArgs {
+    int nk;
+    const long long* mk[MAX_KEYS];
+    const unsigned char* mkmask;
+    const uint64_t* slot_of_out;
+    const long long* n_out_ptr;
+    int key_ctype[MAX_KEYS];
+    void* out_keys[MAX_KEYS];
+    uint32_t* out_key_valid[MAX_KEYS];  // nullptr for non-nullable key columns
+};
+__global__ void eval_mk_keys_kernel(const __grid_constant__ EvalMkKeysArgs a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_out = *a.n_out_ptr;
+    int64_t n_round = (n_out + 31) & ~31ll;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_round; p += stride) {
+        bool in = p < n_out;
+        uint64_t s = in ? a.slot_of_out[p] : 0;
+        unsigned int mask = in ? a.mkmask[s] : 0;
+        for (int j = 0; j < a.nk; j++) {
+            if (in) store_int_typed(a.out_keys[j], a.key_ctype[j], p, a.mk[j][s]);
+            if (a.out_key_valid[j]) {
+                unsigned m = __ballot_sync(0xffffffffu, in && ((mask >> j) & 1));
+                if ((threadIdx.x & 31) == 0) a.out_key_valid[j][p >> 5] = m;
+            }
         }
     }
 }
@@ -945,6 +1100,9 @@ class GroupbyState {
     int sms;
 
     uint64_t cap = 0;
+    int nk = 1;  // number of key columns (2..4 = multi-key table: d_tags / d_mk / d_mkmask instead of d_keys)
+    DevBuf d_tags, d_mk[MAX_KEYS], d_mkmask;
+    DevBuf d_out_mk[MAX_KEYS], d_out_mk_valid[MAX_KEYS];
     DevBuf d_keys;
     std::vector<DevBuf> d_a0, d_a1;
     DevBuf d_counters;
@@ -990,14 +1148,19 @@ class GroupbyState {
                  int device_, int n_pes_, int rank_, int64_t expected_groups, cudaStream_t stream_)
         : device(device_), stream(stream_), n_cols(n_arrs), n_funcs(n_funcs_), dropna(dropna_), parallel(parallel_),
           n_pes(n_pes_), rank(rank_), output_batch_size(out_bs) {
-        B200_REQUIRE(n_keys == 1, "b200 groupby: exactly one key column is supported (multi-key is a 'next' row, SURVEY.md §8f)");
+        B200_REQUIRE(n_keys >= 1 && n_keys <= (uint64_t)MAX_KEYS, "b200 groupby: between 1 and 4 key columns are supported");
+        nk = (int)n_keys;
+        B200_REQUIRE(!(nk > 1 && parallel_ && n_pes_ > 1), "b200 groupby: multi-column keys are not supported on the sharded (parallel) path yet");
         B200_REQUIRE(n_arrs >= 1, "b200 groupby: empty build schema");
         B200_REQUIRE(n_funcs_ <= MAX_OPS, "b200 groupby: too many aggregate functions");
         c_types.assign(ct, ct + n_arrs);
         arr_types.assign(at, at + n_arrs);
-        int kct = c_types[0];
-        B200_REQUIRE(ctype_size(kct) > 0 && !ctype_is_float(kct), "b200 groupby: key column must be an integer/date type");
-        B200_REQUIRE(arr_types[0] == ARR_NUMPY || arr_types[0] == ARR_NULLABLE, "b200 groupby: unsupported key array type");
+        B200_REQUIRE(n_arrs >= nk, "b200 groupby: fewer columns than keys");
+        for (int kc = 0; kc < nk; kc++) {
+            int kct = c_types[kc];
+            B200_REQUIRE(ctype_size(kct) > 0 && !ctype_is_float(kct), "b200 groupby: key columns must be integer/date typed");
+            B200_REQUIRE(arr_types[kc] == ARR_NUMPY || arr_types[kc] == ARR_NULLABLE, "b200 groupby: unsupported key array type");
+        }
         if (!parallel) { n_pes = 1; rank = 0; }
         B200_CUDA(cudaSetDevice(device));
         sms = num_sms(device);
@@ -1007,7 +1170,7 @@ class GroupbyState {
             int n_in = f_in_offsets[j + 1] - f_in_offsets[j];
             B200_REQUIRE(n_in <= 1, "b200 groupby: functions with more than one input column are not supported");
             f.in_col = n_in == 1 ? f_in_cols[f_in_offsets[j]] : -1;
-            if (f.ftype != FT_SIZE) B200_REQUIRE(f.in_col >= 1 && f.in_col < n_arrs, "b200 groupby: bad f_in_cols entry");
+            if (f.ftype != FT_SIZE) B200_REQUIRE(f.in_col >= nk && f.in_col < n_arrs, "b200 groupby: bad f_in_cols entry");
             f.in_ctype = f.in_col >= 0 ? c_types[f.in_col] : CT_INT64;
             f.in_arrtype = f.in_col >= 0 ? arr_types[f.in_col] : ARR_NUMPY;
             B200_REQUIRE(f.in_arrtype == ARR_NUMPY || f.in_arrtype == ARR_NULLABLE, "b200 groupby: unsupported value array type");
@@ -1052,6 +1215,7 @@ class GroupbyState {
         else want = 1ull << 21;
         double t0 = now();
         alloc_table(want, d_keys, d_a0, d_a1);
+        if (nk > 1) alloc_mk(want, d_tags, d_mk, d_mkmask);
         cap = want;
         t_ctor = now() - t0;
     }
@@ -1084,8 +1248,10 @@ class GroupbyState {
 
     void alloc_table(uint64_t c, DevBuf& keys, std::vector<DevBuf>& a0, std::vector<DevBuf>& a1) {
         B200_REQUIRE(c <= (1ull << 32), "b200 groupby: hash table would exceed 2^32 slots");
-        keys.alloc((c + 2) * 8);
-        fill(keys.p, c + 2, (unsigned long long)EMPTY_KEY);
+        if (nk == 1) {
+            keys.alloc((c + 2) * 8);
+            fill(keys.p, c + 2, (unsigned long long)EMPTY_KEY);
+        }
         for (int j = 0; j < n_funcs; j++) {
             a0[j].alloc((c + 2) * 8);
             fill(a0[j].p, c + 2, funcs[j].init0);
@@ -1102,10 +1268,11 @@ class GroupbyState {
     void grow(uint64_t new_cap) {
         double t0 = now();
         struct Acc { double& t; double t0; ~Acc() { t += now() - t0; } } acc{t_grow, t0};
-        DevBuf nk; std::vector<DevBuf> na0(n_funcs), na1(n_funcs);
-        alloc_table(new_cap, nk, na0, na1);
+        if (nk > 1) { grow_mk(new_cap); return; }
+        DevBuf nkeys; std::vector<DevBuf> na0(n_funcs), na1(n_funcs);
+        alloc_table(new_cap, nkeys, na0, na1);
         RehashArgs ra{};
-        ra.old_keys = d_keys.as<long long>(); ra.old_cap = cap; ra.new_keys = nk.as<long long>(); ra.new_cap = new_cap;
+        ra.old_keys = d_keys.as<long long>(); ra.old_cap = cap; ra.new_keys = nkeys.as<long long>(); ra.new_cap = new_cap;
         int n = 0;
         for (int j = 0; j < n_funcs; j++) {
             ra.old_acc[n] = d_a0[j].as<unsigned long long>(); ra.new_acc[n++] = na0[j].as<unsigned long long>();
@@ -1116,10 +1283,70 @@ class GroupbyState {
         launches++;
         B200_CUDA(cudaGetLastError());
         B200_CUDA(cudaStreamSynchronize(stream));  // old arrays are freed below
-        d_keys = std::move(nk);
+        d_keys = std::move(nkeys);
         for (int j = 0; j < n_funcs; j++) { d_a0[j] = std::move(na0[j]); d_a1[j] = std::move(na1[j]); }
         cap = new_cap;
         rebuilds++;
+    }
+
+    // ---- multi-key table management ----
+    void alloc_mk(uint64_t c, DevBuf& tags, DevBuf* mk, DevBuf& mask) {
+        tags.alloc(c * 8);
+        B200_CUDA(cudaMemsetAsync(tags.p, 0, c * 8, stream));
+        for (int j = 0; j < nk; j++) mk[j].alloc(c * 8);
+        mask.alloc(c);
+    }
+    void grow_mk(uint64_t new_cap) {
+        DevBuf ntags, nmk[MAX_KEYS], nmask, dummy;
+        std::vector<DevBuf> na0(n_funcs), na1(n_funcs);
+        alloc_table(new_cap, dummy, na0, na1);
+        alloc_mk(new_cap, ntags, nmk, nmask);
+        RehashMkArgs ra{};
+        ra.nk = nk; ra.old_tags = d_tags.as<unsigned long long>(); ra.old_mask = d_mkmask.as<unsigned char>(); ra.old_cap = cap;
+        ra.tags = ntags.as<unsigned long long>(); ra.mkmask = nmask.as<unsigned char>(); ra.cap = new_cap;
+        ra.counters = d_counters.as<long long>(); ra.group_limit = -1;
+        for (int j = 0; j < nk; j++) { ra.old_mk[j] = d_mk[j].as<long long>(); ra.mk[j] = nmk[j].as<long long>(); }
+        int n = 0;
+        for (int j = 0; j < n_funcs; j++) {
+            ra.old_acc[n] = d_a0[j].as<unsigned long long>(); ra.new_acc[n++] = na0[j].as<unsigned long long>();
+            if (funcs[j].has_a1) { ra.old_acc[n] = d_a1[j].as<unsigned long long>(); ra.new_acc[n++] = na1[j].as<unsigned long long>(); }
+        }
+        ra.n_acc = n;
+        rehash_mk_kernel<<<grid_for((int64_t)cap), 256, 0, stream>>>(ra);
+        launches++;
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaStreamSynchronize(stream));
+        d_tags = std::move(ntags); d_mkmask = std::move(nmask);
+        for (int j = 0; j < nk; j++) d_mk[j] = std::move(nmk[j]);
+        for (int j = 0; j < n_funcs; j++) { d_a0[j] = std::move(na0[j]); d_a1[j] = std::move(na1[j]); }
+        cap = new_cap;
+        rebuilds++;
+    }
+    void consume_mk(const std::vector<const void*>& data, const std::vector<const uint8_t*>& valid, int64_t n) {
+        bool could_fail = (int64_t)(cap / 2) - n_groups_bound < n;
+        if (could_fail) d_fail.ensure(device, (size_t)n * 4);
+        auto launch = [&](const uint32_t* index_list, int64_t rows) {
+            MkArgs a{};
+            a.nk = nk; a.dropna = dropna ? 1 : 0; a.n_rows = rows; a.index_list = index_list;
+            for (int j = 0; j < nk; j++) { a.key_data[j] = data[j]; a.key_valid[j] = valid[j]; a.key_ctype[j] = c_types[j]; a.mk[j] = d_mk[j].as<long long>(); }
+            a.tags = d_tags.as<unsigned long long>(); a.mkmask = d_mkmask.as<unsigned char>(); a.cap = cap;
+            a.counters = d_counters.as<long long>(); a.group_limit = (long long)(cap / 2); a.fail_list = d_fail.as<uint32_t>();
+            a.n_ops = n_funcs;
+            for (int j = 0; j < n_funcs; j++) {
+                const FuncSpec& f = funcs[j];
+                a.ops[j].kind = f.kind; a.ops[j].in_ctype = f.in_ctype;
+                a.ops[j].in_data = f.in_col >= 0 ? data[f.in_col] : nullptr;
+                a.ops[j].in_valid = f.in_col >= 0 ? valid[f.in_col] : nullptr;
+                a.ops[j].a0 = d_a0[j].p; a.ops[j].a1 = f.has_a1 ? d_a1[j].p : nullptr;
+            }
+            groupby_consume_mk_kernel<<<grid_for(rows), 256, 0, stream>>>(a);
+            launches++; consume_launches += index_list == nullptr;
+            B200_CUDA(cudaGetLastError());
+        };
+        launch(nullptr, n);
+        settle(n, could_fail, launch);
+        if (!could_fail) n_groups_bound += n; else n_groups_bound = n_groups;
+        rows_consumed += n;
     }
 
     // After a launch that may have failed rows: grow + replay until every row is in.
@@ -1323,6 +1550,7 @@ class GroupbyState {
     // Consume rows [0, n) of device-resident columns.
     void consume_device_chunk(const std::vector<const void*>& data, const std::vector<const uint8_t*>& valid, int64_t n) {
         if (n == 0) return;
+        if (nk > 1) { consume_mk(data, valid, n); return; }
         // fast path: non-null int64 key + {sum, count/size} over one non-null int64 value column
         bool fast = c_types[0] == CT_INT64 && valid[0] == nullptr && n_funcs >= 1;
         int sum_j = -1, cnt_j = -1, vcol = -1;
@@ -1422,7 +1650,7 @@ class GroupbyState {
         B200_CUDA(cudaSetDevice(device));
         int64_t n = t->n_rows;
         std::vector<bool> used(n_cols, false);
-        used[0] = true;
+        for (int kc = 0; kc < nk; kc++) used[kc] = true;
         for (auto& f : funcs) if (f.in_col >= 0) used[f.in_col] = true;
         for (int c = 0; c < n_cols; c++) {
             if (!used[c]) continue;
@@ -1491,8 +1719,11 @@ class GroupbyState {
         int64_t max_out = n_groups + 2;
         d_slot_of_out.ensure((size_t)max_out * 8);
         B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 16, 0, 8, stream));
-        compact_slots_kernel<<<grid_for((int64_t)cap + 2), 256, 0, stream>>>(d_keys.as<long long>(), cap, d_counters.as<long long>(),
-                                                                                  d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>());
+        if (nk > 1)
+            compact_mk_kernel<<<grid_for((int64_t)cap), 256, 0, stream>>>(d_tags.as<unsigned long long>(), cap, d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>());
+        else
+            compact_slots_kernel<<<grid_for((int64_t)cap + 2), 256, 0, stream>>>(d_keys.as<long long>(), cap, d_counters.as<long long>(),
+                                                                                      d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>());
         launches++;
         B200_CUDA(cudaGetLastError());
         n_out = -1;  // known on the device (counters[2]); the host learns it with the next counter read-back
@@ -1506,13 +1737,26 @@ class GroupbyState {
         compact();
         const int64_t max_out = n_groups + 2;  // exact group count (+ the two special slots) from compact()'s read-back
         EvalArgs e{};
-        e.tkeys = d_keys.as<long long>(); e.cap = cap; e.slot_of_out = d_slot_of_out.as<uint64_t>(); e.n_out_ptr = d_counters.as<long long>() + 2;
+        e.tkeys = nk == 1 ? d_keys.as<long long>() : nullptr; e.cap = cap; e.slot_of_out = d_slot_of_out.as<uint64_t>(); e.n_out_ptr = d_counters.as<long long>() + 2;
         e.key_ctype = c_types[0];
         size_t words = (size_t)((max_out + 31) / 32 + 1);
-        d_out_keys.ensure((size_t)(max_out + 32) * ctype_size(c_types[0]));
-        e.out_keys = d_out_keys.p;
-        bool key_nullable = arr_types[0] == ARR_NULLABLE;
-        if (key_nullable) { d_out_key_valid.ensure(words * 4); e.out_key_valid = d_out_key_valid.as<uint32_t>(); }
+        if (nk == 1) {
+            d_out_keys.ensure((size_t)(max_out + 32) * ctype_size(c_types[0]));
+            e.out_keys = d_out_keys.p;
+            bool key_nullable = arr_types[0] == ARR_NULLABLE;
+            if (key_nullable) { d_out_key_valid.ensure(words * 4); e.out_key_valid = d_out_key_valid.as<uint32_t>(); }
+        } else {
+            EvalMkKeysArgs k{};
+            k.nk = nk; k.mkmask = d_mkmask.as<unsigned char>(); k.slot_of_out = d_slot_of_out.as<uint64_t>(); k.n_out_ptr = d_counters.as<long long>() + 2;
+            for (int j = 0; j < nk; j++) {
+                k.mk[j] = d_mk[j].as<long long>(); k.key_ctype[j] = c_types[j];
+                d_out_mk[j].ensure((size_t)(max_out + 32) * ctype_size(c_types[j]));
+                k.out_keys[j] = d_out_mk[j].p;
+                if (arr_types[j] == ARR_NULLABLE) { d_out_mk_valid[j].ensure(words * 4); k.out_key_valid[j] = d_out_mk_valid[j].as<uint32_t>(); }
+            }
+            eval_mk_keys_kernel<<<grid_for(max_out), 256, 0, stream>>>(k);
+            launches++;
+        }
         e.n_ops = n_funcs;
         for (int j = 0; j < n_funcs; j++) {
             const FuncSpec& f = funcs[j];
@@ -1607,14 +1851,18 @@ class GroupbyState {
         if (bs % 32 != 0 && bs < n_out) bs = (bs + 31) & ~31ll;  // validity bitmaps are sliced at word granularity
         int64_t rows = produce_output ? std::min(bs, n_out - out_cursor) : 0;
         B200_REQUIRE(out->cols != nullptr, "b200 groupby: out->cols must point to n_keys + n_funcs descriptors");
-        out->n_rows = rows; out->n_cols = 1 + n_funcs; out->device = device;
+        out->n_rows = rows; out->n_cols = nk + n_funcs; out->device = device;
         int64_t off = out_cursor;
-        b200_column& k = out->cols[0];
-        k.data = (char*)d_out_keys.p + off * ctype_size(c_types[0]);
-        k.validity = arr_types[0] == ARR_NULLABLE ? d_out_key_valid.as<uint8_t>() + off / 8 : nullptr;
-        k.length = rows; k.c_type = c_types[0]; k.arr_type = arr_types[0];
+        for (int kc = 0; kc < nk; kc++) {
+            b200_column& k = out->cols[kc];
+            const DevBuf& kd = nk == 1 ? d_out_keys : d_out_mk[kc];
+            const DevBuf& kv = nk == 1 ? d_out_key_valid : d_out_mk_valid[kc];
+            k.data = (char*)kd.p + off * ctype_size(c_types[kc]);
+            k.validity = arr_types[kc] == ARR_NULLABLE ? kv.as<uint8_t>() + off / 8 : nullptr;
+            k.length = rows; k.c_type = c_types[kc]; k.arr_type = arr_types[kc];
+        }
         for (int j = 0; j < n_funcs; j++) {
-            b200_column& c = out->cols[1 + j];
+            b200_column& c = out->cols[nk + j];
             c.data = (char*)d_out_data[j].p + off * ctype_size(funcs[j].out_ctype);
             c.validity = funcs[j].out_arrtype == ARR_NULLABLE ? d_out_valid[j].as<uint8_t>() + off / 8 : nullptr;
             c.length = rows; c.c_type = funcs[j].out_ctype; c.arr_type = funcs[j].out_arrtype;

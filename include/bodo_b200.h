@@ -53,8 +53,9 @@ int b200_device_count(void);
 
 /* ---- streaming hash groupby (reference door 1: bodo/libs/streaming/_groupby.cpp) ---- */
 
-/* groupby_state_init_py_entry (_groupby.cpp:4917-4970). Keys are the first n_keys columns of every
- * build batch; ftypes are Bodo_FTypes (groupby/_groupby_ftypes.h:17-110: size=4 sum=6 count=7 mean=14
+/* groupby_state_init_py_entry (_groupby.cpp:4917-4970). Keys are the first n_keys (1..4, integer/date typed;
+ * multi-column keys on the non-sharded path only) columns of every build batch; n_funcs may be 0 (select
+ * distinct / drop_duplicates, reference: physical/aggregate.h:198-227); ftypes are Bodo_FTypes (groupby/_groupby_ftypes.h:17-110: size=4 sum=6 count=7 mean=14
  * min=15 max=16); f_in_offsets/f_in_cols is the CSR map function -> physical input column
  * (streaming/_groupby.h:1059-1070). Arguments of the reference that only concern window functions,
  * MRNF, sort keys and the host operator pool are dropped. `pandas_drop_na`: drop rows with NA keys
@@ -107,7 +108,8 @@ void b200_delete_groupby_state(void* state);
 /* Metrics (subset of GroupbyMetrics, streaming/_groupby.h:106-223): 0 n_groups, 1 table capacity,
  * 2 rows consumed, 3 table rebuilds, 4 kernel launches so far, 5 rows replayed from the fail list,
  * 6 accumulated device time of the consume kernel in microseconds (CUDA events on the state's stream;
- * only when profiling was enabled by querying metric 100 first), 7 consume-kernel launches. */
+ * only when profiling was enabled by querying metric 100 first), 7 consume-kernel launches, 8 SM-partitioned
+ * (SPG) launches, 9 rows/partials replayed from the SPG retry lists, 10 low-cardinality (LC) launches. */
 int64_t b200_groupby_get_metric(void* state, int32_t which);
 
 /* ---- streaming hash join (reference: bodo/libs/streaming/_join.cpp) ---- */

@@ -211,3 +211,46 @@ def test_sm_partitioned_path_skewed_keys(gpu_lib, oracle):
     got = out.to_pandas()
     delete_groupby_state(st)
     assert_frames_equal(positional(got), oracle_groupby_frame(oracle, t, 0, ["sum", "count"], [1, 1]))
+
+
+def test_groupby_drop_duplicates_reference_fixture(gpu_lib):
+    # test_groupby_drop_duplicates (bodo/tests/test_streaming/test_groupby.py:111-177): two key columns, zero functions
+    df = pd.DataFrame({"A": [1, 1, 2, 4, 4, 2], "B": [1, 1, 3, 6, 6, 3]})
+    got = stream_groupby(Table.from_pandas(df), (0, 1), (), (0,), (), batch_size=3)
+    exp = df.drop_duplicates().reset_index(drop=True)
+    assert list(got.columns) == ["A", "B"]
+    g = got.sort_values(["A", "B"]).reset_index(drop=True)
+    np.testing.assert_array_equal(g.to_numpy(), exp.sort_values(["A", "B"]).to_numpy())
+
+
+@pytest.mark.parametrize("dropna", [True, False])
+def test_multi_key_groupby_vs_pandas(gpu_lib, dropna):
+    rng = np.random.default_rng(17)
+    n = 200_000
+    df = pd.DataFrame({
+        "k1": pd.array(rng.integers(0, 300, n), dtype="Int64"),
+        "v": rng.integers(-1000, 1000, n).astype(np.int64),
+        "k2": rng.integers(-5, 5, n).astype(np.int32),
+        "k3": pd.array(rng.integers(0, 3, n), dtype="Int32"),
+        "f": rng.random(n),
+    })
+    df.loc[rng.random(n) < 0.02, "k1"] = pd.NA
+    df.loc[rng.random(n) < 0.02, "k3"] = pd.NA
+    t = Table.from_pandas(df)
+    # keys = (k1, k2, k3) at logical columns (0, 2, 3); tiny expected_groups forces table rebuilds of the multi-key table
+    got = stream_groupby(t, (0, 2, 3), ("sum", "count", "mean", "max", "size"), (0, 1, 2, 3, 4, 4), (1, 1, 4, 4), batch_size=37_000,
+                         dropna=dropna, expected_groups=8, output_batch_size=4096)
+    exp = df.groupby(["k1", "k2", "k3"], dropna=dropna, as_index=False).agg(f0=("v", "sum"), f1=("v", "count"), f2=("f", "mean"), f3=("f", "max"),
+                                                                          f4=("v", "size"))
+    assert len(got) == len(exp)
+    got.columns = list(exp.columns)
+    def canon(d):
+        d = d.copy()
+        for c in d.columns:
+            d[c] = d[c].to_numpy(dtype="float64", na_value=np.nan)
+        return d.sort_values(list(d.columns[:3]), na_position="last").reset_index(drop=True)
+    g, e = canon(got), canon(exp)
+    for c in ("k1", "k2", "k3", "f0", "f1", "f4"):
+        np.testing.assert_array_equal(g[c].to_numpy(), e[c].to_numpy(), err_msg=c)
+    for c in ("f2", "f3"):
+        np.testing.assert_allclose(g[c].to_numpy(), e[c].to_numpy(), rtol=1e-5, atol=1e-8, err_msg=c)
