@@ -631,6 +631,7 @@ constexpr int SPG_PTHREADS = 256;   // K1 (partition) threads per CTA
 constexpr int SPG_PCTAS = 4;        // K1 CTAs per SM (more independent CTAs = barrier / load stalls overlap)
 constexpr int SPG_TILE = 2048;
 constexpr int SPG_MAX_OWNERS = 256;
+constexpr int SPG_STASH = 1024;     // K2: linear-probing stash slots for keys whose two buckets are full
 
 struct SpgArgs {
     const long long* keys;
@@ -897,43 +898,36 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
 }
 
 // K2: one CTA per owner aggregates its bucket in shared memory, then flushes into the global table.
+//
+// Shared table = two-choice bucketed hash table + stash: every key has two candidate buckets of two slots (one 16-byte
+// shared load each), so the hot lookup is two unconditional loads + four compares, no probe loop and no divergence
+// (a linear-probing table spent > 50 % of its issue slots on loop control with ~15 of 32 lanes active,
+// profiles/r01_spg_ncu_summary.txt; a collision-free key set runs the same loop 1.65x faster, scratch/ubench3.cu).
+// Everything else — first appearance of a key (CAS into a free candidate slot), keys whose four candidates are taken
+// (~2 % at this load: linear-probing stash behind the buckets), a full stash (direct global path), a non-zero high word
+// of the sum — is parked and handled once per iteration behind the hot path.  Two racing inserts may put one key into
+// both of its buckets: harmless, both partial sums are flushed into the same global group.
 template <bool HAS_SUM, bool HAS_CNT>
 __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NS = a.ns, tid = threadIdx.x, me = blockIdx.x;
-    long long* skeys = (long long*)smem_raw;      // NS x 8
-    // 16 bytes per slot: key, low 32 bits of the sum, count.  The high word of an addition (value bits 32..63 plus the
-    // carry out of the low word) is almost always zero for small |values| (hi = 0xffffffff and carry = 1 cancel for
-    // small negative ones); when it is not, it is added straight to the global table, which keeps SUM exact mod 2^64.
-    unsigned int* slo = (unsigned int*)(skeys + NS);  // NS x 4
-    unsigned int* scnt = slo + NS;
-    unsigned int* misc = scnt + NS;  // [0] occupied slots
-    // the low word starts at 2^31 (bias) so that sums of small positive AND negative values stay away from the 32-bit
-    // wrap-around points: without it every zero crossing of a running sum would produce a high-word event
-    for (int s = tid; s < NS; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0x80000000u; scnt[s] = 0; }
-    if (tid == 0) misc[0] = 0;
+    const int NS = a.ns, NT = a.ns + SPG_STASH, tid = threadIdx.x, me = blockIdx.x;  // NS bucket slots + stash
+    // 16 bytes per slot: key, low 32 bits of the sum (biased by 2^31 so sums of small positive AND negative values stay away
+    // from the 32-bit wrap points), count.  The high word of an addition (value bits 32..63 plus the carry out of the low
+    // word) is almost always zero; when it is not it is added straight to the global table: SUM stays exact mod 2^64.
+    long long* skeys = (long long*)smem_raw;          // NT x 8
+    unsigned int* slo = (unsigned int*)(skeys + NT);  // NT x 4
+    unsigned int* scnt = slo + NT;
+    for (int s = tid; s < NT; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0x80000000u; scnt[s] = 0; }
     __syncthreads();
-    const unsigned int occ_limit = (unsigned int)(NS - NS / 8);  // keep 1/8 of the slots free so probing stays short
+    const unsigned int NB = (unsigned int)NS / 2;
 
-    // NOTE (measured, r01): forcing the warp to reconverge (__syncwarp) between the probe loop and the atomics makes this
-    // kernel 25 % SLOWER — lanes that leave the loop early overlap their atomics with the other lanes' probes.
-    auto upsert = [&](long long key, long long val) {
-        unsigned int s = spg_slot(spg_hash(key), NS);
-        bool done = false;
-        for (int probes = 0; probes < 256; probes++) {
-            long long kk = skeys[s];
-            if (kk == EMPTY_KEY) {
-                unsigned int t = atomicAdd(&misc[0], 1u);
-                if (t >= occ_limit) { atomicSub(&misc[0], 1u); break; }
-                long long prev = (long long)atomicCAS((unsigned long long*)&skeys[s], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-                if (prev == EMPTY_KEY) { done = true; break; }
-                atomicSub(&misc[0], 1u);
-                kk = prev;
-            }
-            if (kk == key) { done = true; break; }
-            s = s + 1 == (unsigned int)NS ? 0u : s + 1;
-        }
-        if (!done) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, (unsigned long long)val, 1ull); return; }
+    auto buckets = [&](long long key, unsigned int& b1, unsigned int& b2) {
+        const uint64_t h = spg_hash(key);
+        b1 = __umulhi((unsigned int)(h >> 20), NB);
+        b2 = __umulhi((unsigned int)(((h ^ (h >> 31)) * 0xBF58476D1CE4E5B9ULL) >> 32), NB);
+        b2 = b2 == b1 ? (b1 + 1 == NB ? 0u : b1 + 1) : b2;
+    };
+    auto add = [&](int s, long long key, long long val) {
         if (HAS_SUM) {
             unsigned int lo = (unsigned int)(unsigned long long)val, hi = (unsigned int)((unsigned long long)val >> 32);
             unsigned int old = atomicAdd(&slo[s], lo);
@@ -942,25 +936,72 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
         }
         if (HAS_CNT) atomicAdd(&scnt[s], 1u);
     };
+    // slow path: claim a free candidate slot, else find-or-insert in the stash, else the direct global path
+    auto slow_upsert = [&](long long key, long long val) {
+        unsigned int b1, b2;
+        buckets(key, b1, b2);
+        const unsigned long long uk = (unsigned long long)key;
+        const unsigned int cand[4] = {2 * b1, 2 * b1 + 1, 2 * b2, 2 * b2 + 1};
+        int s = -1;
+#pragma unroll
+        for (int c = 0; c < 4 && s < 0; c++) {
+            unsigned long long old = atomicCAS((unsigned long long*)&skeys[cand[c]], (unsigned long long)EMPTY_KEY, uk);
+            if (old == (unsigned long long)EMPTY_KEY || old == uk) s = (int)cand[c];
+        }
+        if (s < 0) {
+            unsigned int st = (unsigned int)NS + ((unsigned int)(spg_hash(key) >> 12) & (SPG_STASH - 1));
+            for (int probes = 0; probes < SPG_STASH && s < 0; probes++) {
+                unsigned long long kk = (unsigned long long)skeys[st];
+                if (kk == (unsigned long long)EMPTY_KEY) {
+                    unsigned long long old = atomicCAS((unsigned long long*)&skeys[st], (unsigned long long)EMPTY_KEY, uk);
+                    if (old == (unsigned long long)EMPTY_KEY) { s = (int)st; break; }
+                    kk = old;
+                }
+                if (kk == uk) { s = (int)st; break; }
+                st = st + 1 == (unsigned int)NS + SPG_STASH ? (unsigned int)NS : st + 1;
+            }
+        }
+        if (s < 0) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, (unsigned long long)val, 1ull); return; }
+        add(s, key, val);
+    };
 
     unsigned long long n_in = a.bucket_cnt[me];
     if (n_in > (unsigned long long)a.bucket_cap) n_in = (unsigned long long)a.bucket_cap;
     const longlong2* src = a.bucket + (size_t)me * a.bucket_cap;
-    constexpr int U = 4;  // independent bucket loads in flight per thread (8 measured slower: 62 registers)
+    constexpr int U = 4;  // independent bucket loads in flight per thread
     for (unsigned long long p0 = tid; p0 < n_in; p0 += (unsigned long long)U * SPG_THREADS) {
         longlong2 row[U];
+        int sl[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             unsigned long long p = p0 + (unsigned long long)u * SPG_THREADS;
             row[u] = p < n_in ? __ldcs(src + p) : make_longlong2(EMPTY_KEY, 0);
         }
 #pragma unroll
-        for (int u = 0; u < U; u++)
-            if (row[u].x != EMPTY_KEY) upsert(row[u].x, row[u].y);
+        for (int u = 0; u < U; u++) {  // hot lookups: branch-free
+            unsigned int b1, b2;
+            buckets(row[u].x, b1, b2);
+            const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(skeys + 2 * b1);
+            const ulonglong2 k2 = *reinterpret_cast<const ulonglong2*>(skeys + 2 * b2);
+            const unsigned long long uk = (unsigned long long)row[u].x;
+            sl[u] = k1.x == uk ? (int)(2 * b1) : k1.y == uk ? (int)(2 * b1 + 1) : k2.x == uk ? (int)(2 * b2) : k2.y == uk ? (int)(2 * b2 + 1) : -1;
+            if (row[u].x == EMPTY_KEY) sl[u] = -2;  // padding lane
+        }
+        long long pk = 0, pv = 0;
+        bool parked = false;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (sl[u] >= 0) add(sl[u], row[u].x, row[u].y);
+            else if (sl[u] == -1) {
+                if (!parked) { pk = row[u].x; pv = row[u].y; parked = true; }
+                else slow_upsert(row[u].x, row[u].y);  // second slow row of this thread in one iteration: rare
+            }
+        }
+        if (parked) slow_upsert(pk, pv);
     }
     __syncthreads();
     // flush the shared table into the state's global table
-    for (int s = tid; s < NS; s += SPG_THREADS) {
+    for (int s = tid; s < NT; s += SPG_THREADS) {
         long long key = skeys[s];
         if (key == EMPTY_KEY) continue;
         unsigned long long sum = (unsigned long long)slo[s] - 0x80000000ull;  // remove the bias (wraps mod 2^64)
@@ -1390,8 +1431,8 @@ class GroupbyState {
         int max_smem = 0;
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
         if (sms > SPG_MAX_OWNERS - 1 || max_smem < 64 * 1024) return false;
-        spg_ns = (int)(((size_t)max_smem - 64) / 16) & ~1;
-        spg_smem = (size_t)spg_ns * 16 + 16;
+        spg_ns = ((int)(((size_t)max_smem - 64) / 16) - SPG_STASH) & ~1;
+        spg_smem = (size_t)(spg_ns + SPG_STASH) * 16 + 16;
         const void* fns[3] = {(const void*)spg_aggregate_kernel<true, true>, (const void*)spg_aggregate_kernel<true, false>,
                               (const void*)spg_aggregate_kernel<false, true>};
         for (auto f : fns)
@@ -1420,8 +1461,8 @@ class GroupbyState {
     static size_t spg_tma_smem() { return (size_t)SPG_TILE * (16 * SPG_TBUFS + 16 + 1) + SPG_MAX_OWNERS * 8 + 16 + (2 * SPG_MAX_OWNERS + 4) * 4 + 256; }
     static size_t spg_part_smem() { return (size_t)SPG_TILE * 17 + SPG_MAX_OWNERS * 8 + (2 * SPG_MAX_OWNERS + 4) * 4 + 64; }
     bool lc_pick(int64_t est) { lowcard_small = est <= LC_SLOTS_SMALL / 4; return lc_enabled && est <= LC_SLOTS_BIG / 4; }
-    // groups the shared-memory tables of all owners can hold together (7/8 of the slots, see occ_limit)
-    int64_t spg_group_capacity() const { return (int64_t)spg_owners * (spg_ns - spg_ns / 8); }
+    // groups the shared-memory tables of all owners are expected to hold together (two-choice buckets work well up to ~70 %)
+    int64_t spg_group_capacity() const { return (int64_t)spg_owners * (spg_ns * 7 / 10); }
 
     // One SPG launch pair in flight while the host inspects the previous one (two retry lists / counter slots), so
     // the GPU never idles on the host's counter read-back.
