@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -924,7 +925,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     auto buckets = [&](long long key, unsigned int& b1, unsigned int& b2) {
         const uint64_t h = spg_hash(key);
         b1 = __umulhi((unsigned int)(h >> 20), NB);
-        b2 = __umulhi((unsigned int)(((h ^ (h >> 31)) * 0xBF58476D1CE4E5B9ULL) >> 32), NB);
+        b2 = __umulhi(((unsigned int)h ^ (unsigned int)(h >> 44)) * 0x9E3779B1u, NB);  // low word of h remixed: independent of b1's bits 20..51 enough
         b2 = b2 == b1 ? (b1 + 1 == NB ? 0u : b1 + 1) : b2;
     };
     auto add = [&](int s, long long key, long long val) {
@@ -969,13 +970,14 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     if (n_in > (unsigned long long)a.bucket_cap) n_in = (unsigned long long)a.bucket_cap;
     const longlong2* src = a.bucket + (size_t)me * a.bucket_cap;
     constexpr int U = 4;  // independent bucket loads in flight per thread
-    for (unsigned long long p0 = tid; p0 < n_in; p0 += (unsigned long long)U * SPG_THREADS) {
+    auto process = [&](unsigned long long base, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;  // FULL: all U rows of every thread are in range (no padding checks)
         longlong2 row[U];
         int sl[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            unsigned long long p = p0 + (unsigned long long)u * SPG_THREADS;
-            row[u] = p < n_in ? __ldcs(src + p) : make_longlong2(EMPTY_KEY, 0);
+            unsigned long long p = base + tid + (unsigned long long)u * SPG_THREADS;
+            row[u] = (FULL || p < n_in) ? __ldcs(src + p) : make_longlong2(EMPTY_KEY, 0);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {  // hot lookups: branch-free
@@ -985,7 +987,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
             const ulonglong2 k2 = *reinterpret_cast<const ulonglong2*>(skeys + 2 * b2);
             const unsigned long long uk = (unsigned long long)row[u].x;
             sl[u] = k1.x == uk ? (int)(2 * b1) : k1.y == uk ? (int)(2 * b1 + 1) : k2.x == uk ? (int)(2 * b2) : k2.y == uk ? (int)(2 * b2 + 1) : -1;
-            if (row[u].x == EMPTY_KEY) sl[u] = -2;  // padding lane
+            if (!FULL && row[u].x == EMPTY_KEY) sl[u] = -2;  // padding lane
         }
         long long pk = 0, pv = 0;
         bool parked = false;
@@ -998,7 +1000,11 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
             }
         }
         if (parked) slow_upsert(pk, pv);
-    }
+    };
+    const unsigned long long step = (unsigned long long)U * SPG_THREADS;
+    const unsigned long long n_full = n_in / step * step;
+    for (unsigned long long base = 0; base < n_full; base += step) process(base, std::true_type{});
+    if (n_full < n_in) process(n_full, std::false_type{});
     __syncthreads();
     // flush the shared table into the state's global table
     for (int s = tid; s < NT; s += SPG_THREADS) {
