@@ -882,13 +882,14 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
             stage[p] = make_longlong2(kb[j], HAS_SUM ? vb[j] : 0);
             stage_owner[p] = (unsigned char)o[r];
         }
-        if (tid >= SPG_TTHREADS - G) gbase[tid - (SPG_TTHREADS - G)] = my_gbase;
+        // publish run start minus local start, so the copy-out computes its destination with one add
+        if (tid >= SPG_TTHREADS - G) { int ow = tid - (SPG_TTHREADS - G); gbase[ow] = my_gbase - lbase[ow]; }
         __syncthreads();  // raw buffer b is free from here on
         if (SPG_TBUFS == 1 && tn < n_tiles) issue(tn, 0);  // single buffer: the next tile streams in during the copy-out
         const unsigned int n_tile = lbase[G];
         for (unsigned int p = tid; p < n_tile; p += SPG_TTHREADS) {
             unsigned int ow = stage_owner[p];
-            unsigned long long off = gbase[ow] + (p - lbase[ow]);
+            unsigned long long off = gbase[ow] + p;
             longlong2 row = stage[p];
             if (off < (unsigned long long)a.bucket_cap) a.bucket[(size_t)ow * a.bucket_cap + off] = row;
             else spg_direct_apply<HAS_SUM, HAS_CNT>(a, row.x, (unsigned long long)row.y, 1ull);
