@@ -128,14 +128,15 @@ class GroupbyState:
         dev = torch.device("cuda", self.device)
         words = row_bytes // 8
         n_send = sum(send_counts)
+        # counts travel as one small all-gather of the n_pes x n_pes matrix (mpi_comm_info's MPI_Alltoall,
+        # _shuffle.cpp:210-213), issued asynchronously so it overlaps the pack kernel
+        sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        allc = torch.empty(self.n_pes * self.n_pes, dtype=torch.int64, device=dev)
+        work = dist.all_gather_into_tensor(allc, sc, group=self.process_group, async_op=True)
         send = torch.empty((max(n_send, 1), words), dtype=torch.int64, device=dev)
         _lib.check(L.b200_groupby_shuffle_pack(h, ffi.cast("void*", send.data_ptr())), "groupby shuffle pack")
         mark()
-        # counts travel as one small all-gather of the n_pes x n_pes matrix (mpi_comm_info's MPI_Alltoall,
-        # _shuffle.cpp:210-213); b200_groupby_shuffle_pack returned with its stream drained, so `send` is complete
-        sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
-        allc = torch.empty(self.n_pes * self.n_pes, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allc, sc, group=self.process_group)
+        work.wait()
         recv_counts = allc.view(self.n_pes, self.n_pes)[:, self.rank].tolist()
         mark()
         n_recv = sum(recv_counts)
