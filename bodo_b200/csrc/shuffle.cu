@@ -161,6 +161,30 @@ __global__ void pack_segment_bitmaps_kernel(const uint8_t* valid_bytes, const lo
     }
 }
 
+// Receive side of the shuffle: the per-source validity segments (each padded to a byte boundary, in source-rank order)
+// become one contiguous Arrow bitmap for the received rows.
+__global__ void merge_segment_bitmaps_kernel(const uint8_t* __restrict__ in, const long long* __restrict__ row_off /* n_src + 1 */,
+                                             const long long* __restrict__ byte_off /* n_src */, int n_src, uint32_t* out_words) {
+    __shared__ long long s_row[MAX_PES + 1];
+    __shared__ long long s_byte[MAX_PES];
+    for (int j = threadIdx.x; j <= n_src; j += blockDim.x) s_row[j] = row_off[j];
+    for (int j = threadIdx.x; j < n_src; j += blockDim.x) s_byte[j] = byte_off[j];
+    __syncthreads();
+    const long long n = s_row[n_src];
+    const long long n_round = (n + 31) & ~31ll;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_round; i += (long long)gridDim.x * blockDim.x) {
+        bool bit = false;
+        if (i < n) {
+            int lo = 0, hi = n_src - 1;  // last source whose first row is <= i
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_row[mid] <= i) lo = mid; else hi = mid - 1; }
+            long long r = i - s_row[lo];
+            bit = (in[s_byte[lo] + (r >> 3)] >> (r & 7)) & 1;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, bit);
+        if ((threadIdx.x & 31) == 0) out_words[i >> 5] = m;
+    }
+}
+
 struct StreamBuf {  // stream-ordered scratch allocation
     void* p = nullptr;
     cudaStream_t s;
@@ -253,6 +277,25 @@ int b200_shuffle_partition(const b200_table* in_table, int64_t n_keys, int32_t n
     try {
         B200_REQUIRE(in_table && out && send_counts, "b200_shuffle_partition: null argument");
         b200::shuffle_partition(in_table, n_keys, n_pes, out, send_counts, nullptr, (cudaStream_t)stream);
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+int b200_merge_segment_bitmaps(const uint8_t* segments, const int64_t* counts, int32_t n_src, uint8_t* out_bitmap, int32_t device, void* stream) {
+    try {
+        B200_REQUIRE(segments && counts && out_bitmap && n_src >= 1 && n_src <= b200::MAX_PES, "b200_merge_segment_bitmaps: bad arguments");
+        B200_CUDA(cudaSetDevice(device));
+        std::vector<long long> row_off(n_src + 1, 0), byte_off(n_src, 0);
+        long long bytes = 0;
+        for (int j = 0; j < n_src; j++) { row_off[j + 1] = row_off[j] + counts[j]; byte_off[j] = bytes; bytes += (counts[j] + 7) >> 3; }
+        if (row_off[n_src] == 0) return 0;
+        cudaStream_t st = (cudaStream_t)stream;
+        b200::StreamBuf d_row((size_t)(n_src + 1) * 8, st), d_byte((size_t)n_src * 8, st);
+        B200_CUDA(cudaMemcpyAsync(d_row.p, row_off.data(), (size_t)(n_src + 1) * 8, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(d_byte.p, byte_off.data(), (size_t)n_src * 8, cudaMemcpyHostToDevice, st));
+        b200::merge_segment_bitmaps_kernel<<<b200::num_sms(device) * 4, 256, 0, st>>>(segments, d_row.as<long long>(), d_byte.as<long long>(), n_src, (uint32_t*)out_bitmap);
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaStreamSynchronize(st));  // row_off / byte_off are stack buffers
         return 0;
     } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
 }

@@ -98,8 +98,20 @@ def exchange_partitioned(buffers: Sequence, send_counts: Sequence[int], validity
 
 
 def merge_segment_bitmaps(bitmap, counts: Sequence[int]):
-    """Concatenate per-source byte-padded bitmaps (one per sending rank) into one contiguous Arrow bitmap."""
+    """Concatenate per-source byte-padded bitmaps (one per sending rank) into one contiguous Arrow bitmap.
+    CUDA tensors go through b200_merge_segment_bitmaps (csrc/shuffle.cu); the numpy branch only serves the CPU (gloo)
+    tests of the exchange logic."""
     import torch
+
+    if bitmap.is_cuda:
+        n = int(sum(counts))
+        out = torch.zeros(((n + 31) // 32 + 2) * 4, dtype=torch.uint8, device=bitmap.device)
+        cnt = ffi.new("int64_t[]", [int(c) for c in counts])
+        _lib.check(_lib.lib().b200_merge_segment_bitmaps(ffi.cast("uint8_t*", bitmap.data_ptr()), cnt, len(counts),
+                                                         ffi.cast("uint8_t*", out.data_ptr()), bitmap.device.index,
+                                                         ffi.cast("void*", torch.cuda.current_stream(bitmap.device).cuda_stream)),
+                   "merge segment bitmaps")
+        return out
 
     bits = []
     off = 0

@@ -163,6 +163,12 @@ int b200_shuffle_partition_perm(const b200_table* in_table, int64_t n_keys, int3
                                 b200_table* out, int64_t* send_counts, int64_t* perm_out_dev,
                                 void* stream);
 
+/* Receive side of shuffle_table: turns the n_src per-source validity segments (each ceil(counts[j]/8) bytes, back to
+ * back, in source-rank order — what the all-to-all-v of the per-destination bitmaps delivers) into one contiguous Arrow
+ * bitmap of sum(counts) rows.  out_bitmap must hold 4 * ceil(sum(counts) / 32) bytes on `device`. */
+int b200_merge_segment_bitmaps(const uint8_t* segments, const int64_t* counts, int32_t n_src,
+                               uint8_t* out_bitmap, int32_t device, void* stream);
+
 /* ---- helpers for host code that does not link CUDA ---- */
 void* b200_device_malloc(int32_t device, int64_t nbytes);
 void b200_device_free(int32_t device, void* p);

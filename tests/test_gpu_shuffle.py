@@ -61,3 +61,16 @@ def test_partition_bit_identical_to_oracle(gpu_lib, oracle, n_pes, n):
                 np.testing.assert_array_equal(seg, mask[off_rows: off_rows + cnt])
                 off_rows += cnt
                 off_bytes += (cnt + 7) // 8
+
+
+@pytest.mark.parametrize("counts", [[5], [0, 9, 0], [8, 8, 8], [1, 31, 32, 33, 0, 70001], [3] * 64])
+def test_merge_segment_bitmaps(gpu_lib, counts):
+    from bodo_b200.shuffle import merge_segment_bitmaps
+    rng = np.random.default_rng(sum(counts))
+    masks = [rng.random(c) > 0.4 for c in counts]
+    segs = [np.packbits(m, bitorder="little") for m in masks]
+    buf = np.concatenate(segs + [np.zeros(8, dtype=np.uint8)])
+    out = merge_segment_bitmaps(torch.from_numpy(buf).cuda(), counts).cpu().numpy()
+    n = sum(counts)
+    got = np.unpackbits(out, bitorder="little")[:n].astype(bool)
+    np.testing.assert_array_equal(got, np.concatenate(masks) if n else np.zeros(0, dtype=bool))
