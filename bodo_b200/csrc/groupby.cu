@@ -654,6 +654,8 @@ struct SpgArgs {
     long long* retry_ctr;       // number of rows in `retry`
     int sum_first;              // order of the two accumulators in the wire format
     int ns;                     // shared-memory table slots (K2)
+    int n_pass;                 // K2 passes over each owner bucket (pass p keeps the keys of sub-range p): > 1 when the
+                                // estimated cardinality exceeds what the shared tables hold at once
 };
 
 // cheap in-kernel hash for owner / shared-table slot (placement inside one GPU is free to choose; the rank
@@ -919,9 +921,8 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     long long* skeys = (long long*)smem_raw;          // NT x 8
     unsigned int* slo = (unsigned int*)(skeys + NT);  // NT x 4
     unsigned int* scnt = slo + NT;
-    for (int s = tid; s < NT; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0x80000000u; scnt[s] = 0; }
-    __syncthreads();
     const unsigned int NB = (unsigned int)NS / 2;
+    const unsigned int NP = (unsigned int)a.n_pass, GP = (unsigned int)gridDim.x * NP;
 
     auto buckets = [&](long long key, unsigned int& b1, unsigned int& b2) {
         const uint64_t h = spg_hash(key);
@@ -971,7 +972,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     if (n_in > (unsigned long long)a.bucket_cap) n_in = (unsigned long long)a.bucket_cap;
     const longlong2* src = a.bucket + (size_t)me * a.bucket_cap;
     constexpr int U = 4;  // independent bucket loads in flight per thread
-    auto process = [&](unsigned long long base, auto full_tag) {
+    auto process = [&](unsigned long long base, unsigned int pass, auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;  // FULL: all U rows of every thread are in range (no padding checks)
         longlong2 row[U];
         int sl[U];
@@ -989,6 +990,8 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
             const unsigned long long uk = (unsigned long long)row[u].x;
             sl[u] = k1.x == uk ? (int)(2 * b1) : k1.y == uk ? (int)(2 * b1 + 1) : k2.x == uk ? (int)(2 * b2) : k2.y == uk ? (int)(2 * b2 + 1) : -1;
             if (!FULL && row[u].x == EMPTY_KEY) sl[u] = -2;  // padding lane
+            // multi-pass: owner = mulhi(hash_hi, G) = mulhi(hash_hi, G * NP) / NP; this pass keeps sub-range `pass` only
+            if (NP > 1 && __umulhi((unsigned int)(spg_hash(row[u].x) >> 32), GP) - (unsigned int)me * NP != pass) sl[u] = -2;
         }
         long long pk = 0, pv = 0;
         bool parked = false;
@@ -1004,15 +1007,20 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     };
     const unsigned long long step = (unsigned long long)U * SPG_THREADS;
     const unsigned long long n_full = n_in / step * step;
-    for (unsigned long long base = 0; base < n_full; base += step) process(base, std::true_type{});
-    if (n_full < n_in) process(n_full, std::false_type{});
-    __syncthreads();
-    // flush the shared table into the state's global table
-    for (int s = tid; s < NT; s += SPG_THREADS) {
-        long long key = skeys[s];
-        if (key == EMPTY_KEY) continue;
-        unsigned long long sum = (unsigned long long)slo[s] - 0x80000000ull;  // remove the bias (wraps mod 2^64)
-        spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, sum, (unsigned long long)scnt[s]);
+    for (unsigned int pass = 0; pass < NP; pass++) {
+        for (int s = tid; s < NT; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0x80000000u; scnt[s] = 0; }
+        __syncthreads();
+        for (unsigned long long base = 0; base < n_full; base += step) process(base, pass, std::true_type{});
+        if (n_full < n_in) process(n_full, pass, std::false_type{});
+        __syncthreads();
+        // flush the shared table into the state's global table
+        for (int s = tid; s < NT; s += SPG_THREADS) {
+            long long key = skeys[s];
+            if (key == EMPTY_KEY) continue;
+            unsigned long long sum = (unsigned long long)slo[s] - 0x80000000ull;  // remove the bias (wraps mod 2^64)
+            spg_direct_apply<HAS_SUM, HAS_CNT>(a, key, sum, (unsigned long long)scnt[s]);
+        }
+        __syncthreads();
     }
 }
 
@@ -1465,6 +1473,13 @@ class GroupbyState {
     }
 
     bool spg_use_tma = true, lc_enabled = true, lowcard_small = false;
+    int spg_passes = 1;
+    static constexpr int SPG_MAX_PASSES = 24;
+    // K2 passes needed for `est` groups (each pass holds spg_group_capacity() groups); 0 = too many for the SPG path
+    int spg_pass_count(int64_t est) const {
+        int64_t p = (est + spg_group_capacity() - 1) / spg_group_capacity();
+        return p <= 1 ? 1 : (p <= SPG_MAX_PASSES ? (int)p : 0);
+    }
     static size_t spg_tma_smem() { return (size_t)SPG_TILE * (16 * SPG_TBUFS + 16 + 1) + SPG_MAX_OWNERS * 8 + 16 + (2 * SPG_MAX_OWNERS + 4) * 4 + 256; }
     static size_t spg_part_smem() { return (size_t)SPG_TILE * 17 + SPG_MAX_OWNERS * 8 + (2 * SPG_MAX_OWNERS + 4) * 4 + 64; }
     bool lc_pick(int64_t est) { lowcard_small = est <= LC_SLOTS_SMALL / 4; return lc_enabled && est <= LC_SLOTS_BIG / 4; }
@@ -1547,7 +1562,7 @@ class GroupbyState {
             a.retry_ctr = d_counters.as<long long>() + 1 + 5 * slot;
             a.bucket = d_bucket.as<longlong2>(); a.bucket_cnt = d_bucket_cnt.as<unsigned long long>(); a.bucket_cap = bucket_cap;
             a.retry = d_retry2[slot].as<unsigned long long>();
-            a.sum_first = (sum_j >= 0 && cnt_j >= 0 && sum_j < cnt_j) ? 1 : 0; a.ns = spg_ns;
+            a.sum_first = (sum_j >= 0 && cnt_j >= 0 && sum_j < cnt_j) ? 1 : 0; a.ns = spg_ns; a.n_pass = spg_passes;
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (profiling) { B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1)); B200_CUDA(cudaEventRecord(ev0, stream)); }
             if (lowcard) {
@@ -1626,11 +1641,12 @@ class GroupbyState {
                 est = n_groups;
                 if (prefix == n) return;
                 for (int c = 0; c < n_cols; c++) if (data[c]) d2[c] = (const char*)data[c] + prefix * ctype_size(c_types[c]);
-                if (est <= spg_group_capacity()) consume_spg((const long long*)d2[0], vcol >= 0 ? (const long long*)d2[vcol] : nullptr, n - prefix, sum_j, cnt_j, lc_pick(est));
+                if (spg_pass_count(est) > 0) { spg_passes = spg_pass_count(est); consume_spg((const long long*)d2[0], vcol >= 0 ? (const long long*)d2[vcol] : nullptr, n - prefix, sum_j, cnt_j, lc_pick(est)); }
                 else consume_direct(d2, v2, n - prefix, fast, sum_j, cnt_j, vcol, false);
                 return;
             }
-            if (force || est <= spg_group_capacity()) {
+            if (force || spg_pass_count(est) > 0) {
+                spg_passes = std::max(1, spg_pass_count(est));
                 consume_spg((const long long*)data[0], vcol >= 0 ? (const long long*)data[vcol] : nullptr, n, sum_j, cnt_j, est > 0 && lc_pick(est));
                 return;
             }

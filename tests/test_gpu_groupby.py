@@ -139,7 +139,7 @@ def test_unsupported_function_fails_loudly(gpu_lib):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("n_groups,hint", [(1000, 0), (50_000, 50_000), (1_000_000, 1_000_000), (3_000_000, 16)])
+@pytest.mark.parametrize("n_groups,hint", [(1000, 0), (50_000, 50_000), (1_000_000, 1_000_000), (3_000_000, 16), (3_000_000, 3_000_000)])
 @pytest.mark.parametrize("funcs", [("sum", "count"), ("count", "sum"), ("sum",), ("size",)])
 def test_sm_partitioned_path_vs_oracle(gpu_lib, oracle, n_groups, hint, funcs):
     # >= 1 Mi-row device batches of the headline shape take the SM-partitioned kernel (when its estimate of the
