@@ -1429,7 +1429,7 @@ class GroupbyState {
     }
 
     // ---- SM-partitioned fast path (SPG) ----
-    static constexpr int64_t SPG_LAUNCH_ROWS = 1ll << 26;
+    static constexpr int64_t SPG_LAUNCH_ROWS = 1ll << 27;
     PooledBuf d_bucket;
     DevBuf d_bucket_cnt;
     int spg_owners = 0, spg_ns = 0;
