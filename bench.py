@@ -35,7 +35,9 @@ BYTES_PER_ROW = 16  # algorithmic bytes of the hash-aggregate scan (SURVEY.md §
 # spg: profiles/r01_spg_ncu_summary.txt, K1 1.074+1.019 GB + K2 1.123+0.004 GB per 2^26-row launch pair (3x the
 # algorithmic 1.074 GB by design: rows are written to and re-read from owner buckets).
 # direct: profiles/r01_direct_ncu_summary.txt (2^27-row launch, bucketized variant): 10.99 + 0.18 GB.
-TRAFFIC_PER_LAUNCH = {"spg": 3.220e9, "direct": 11.17e9}
+# Both are DRAM bytes per ROW of a launch (measured bytes / rows of the captured launch); one launch of the timed run
+# moves that figure x its own row count (launches are 2^27 rows now, the captures above were taken on 2^26 / 2^27).
+TRAFFIC_PER_ROW = {"spg": 3.220e9 / (1 << 26), "direct": 11.17e9 / (1 << 27)}
 
 
 def parse_args():
@@ -292,8 +294,8 @@ def main():
     n_launch = max(stats.get("consume_launches", 1), 1)
     achieved = (BYTES_PER_ROW * n_local / 1e9) / (kern_us * 1e-6) if kern_us else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": TRAFFIC_PER_LAUNCH.get("spg" if stats.get("spg_launches") else "direct"), "peak_kind": peak_kind,
-                "kernel": ("spg_partition_kernel<true,true> + spg_aggregate_kernel<true,true> (one launch = the pair)"
+                "traffic": TRAFFIC_PER_ROW["spg" if stats.get("spg_launches") else "direct"] * n_local / n_launch, "peak_kind": peak_kind,
+                "kernel": ("spg_partition_tma_kernel<true,true> + spg_aggregate_kernel<true,true> (one launch = the pair)"
                            if stats.get("spg_launches") else "groupby_consume_i64_sumcount_kernel<true,true>"),
                 "launches_per_step": n_launch, "avg_launch_ms": kern_us / 1e3 / n_launch,
                 "algorithmic_bytes_per_launch": BYTES_PER_ROW * n_local / n_launch}

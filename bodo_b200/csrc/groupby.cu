@@ -632,6 +632,10 @@ constexpr int SPG_PTHREADS = 256;   // K1 (partition) threads per CTA
 constexpr int SPG_PCTAS = 4;        // K1 CTAs per SM (more independent CTAs = barrier / load stalls overlap)
 constexpr int SPG_TILE = 2048;
 constexpr int SPG_MAX_OWNERS = 256;
+// K1 reserves one run per owner per tile with a global atomic on the owner's row counter: ~10^7 atomics per launch.  With
+// the 148 counters packed into ten cache lines K1's speed depended on where the array happened to land (0.80 ms against
+// 1.00 ms per 2^27 rows for the same SASS after an unrelated allocation moved it), so every counter gets its own line.
+constexpr int SPG_CNT_STRIDE = 16;
 constexpr int SPG_STASH = 1024;     // K2: linear-probing stash slots for keys whose two buckets are full
 
 struct SpgArgs {
@@ -648,7 +652,8 @@ struct SpgArgs {
     long long group_limit;
     // owner buckets
     longlong2* bucket;            // [n_owners][bucket_cap]
-    unsigned long long* bucket_cnt;  // [n_owners] rows appended (may exceed bucket_cap: the excess went the direct way)
+    unsigned long long* bucket_cnt;  // [n_owners * SPG_CNT_STRIDE] rows appended per owner (may exceed bucket_cap: the excess
+                                     // went the direct way); one counter per 128-byte line, see SPG_CNT_STRIDE
     long long bucket_cap;
     unsigned long long* retry;  // partial-aggregate rows [key][1][a0 of func 0][a0 of func 1]
     long long* retry_ctr;       // number of rows in `retry`
@@ -656,6 +661,8 @@ struct SpgArgs {
     int ns;                     // shared-memory table slots (K2)
     int n_pass;                 // K2 passes over each owner bucket (pass p keeps the keys of sub-range p): > 1 when the
                                 // estimated cardinality exceeds what the shared tables hold at once
+    const long long* hot_tab;   // [SPG_HOT_SLOTS] heavy-hitter keys found by spg_hot_sample_kernel (EMPTY_KEY = free), or null
+    const int* n_hot;           // number of keys in hot_tab (device memory: K1 reads it, the host never waits for it)
 };
 
 // cheap in-kernel hash for owner / shared-table slot (placement inside one GPU is free to choose; the rank
@@ -685,6 +692,74 @@ __device__ __forceinline__ void spg_direct_apply(const SpgArgs& a, long long key
     }
     if (HAS_SUM && sum) atomicAdd(a.acc_sum + sl, sum);
     if (HAS_CNT && cnt) atomicAdd(a.acc_cnt + sl, cnt);
+}
+
+// ---- heavy hitters (skewed keys) ----------------------------------------------------------------------------
+// A key that carries more than ~1/1024 of the rows (Zipf-like inputs: the top key of Zipf(1.1) over 1 M groups carries
+// 12 %) would overload its owner: the bucket overflows into the direct path, where every row is a global atomic on ONE
+// address (measured 10 Grows/s against 88 uniform).  Such keys are found once per operator state by counting a strided
+// sample of the first launch (spg_hot_sample_kernel) and are then aggregated inside K1, in a per-CTA shared-memory
+// accumulator table (two-slot buckets: one 16-byte load per row), and never reach the owner buckets.
+constexpr int SPG_HOT_SLOTS = 128, SPG_HOT_BUCKETS = SPG_HOT_SLOTS / 2;
+constexpr int SPG_HOT_SAMPLE = 1 << 15;  // sampled rows (one CTA counts them: the cost is per operator state, ~0.1 ms)
+constexpr int SPG_HOT_TAB = 8192;        // counting-table slots of the sample kernel
+constexpr size_t SPG_HOT_SAMPLE_SMEM = (size_t)SPG_HOT_TAB * 12 + SPG_HOT_SLOTS * 8;
+__device__ __forceinline__ unsigned int spg_hot_bucket(uint64_t h) { return (unsigned int)(h >> 8) & (SPG_HOT_BUCKETS - 1); }
+
+__global__ void __launch_bounds__(1024, 1) spg_hot_sample_kernel(const long long* keys, int64_t n_rows, long long* hot_tab, int* n_hot) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    long long* tk = (long long*)smem_raw;                  // SPG_HOT_TAB keys
+    unsigned int* tc = (unsigned int*)(tk + SPG_HOT_TAB);  // their sample counts
+    long long* hk = (long long*)(tc + SPG_HOT_TAB);        // SPG_HOT_SLOTS: the hot table being built
+    __shared__ unsigned int fill, nh;
+    const int tid = threadIdx.x;
+    for (int s = tid; s < SPG_HOT_TAB; s += 1024) { tk[s] = EMPTY_KEY; tc[s] = 0; }
+    for (int s = tid; s < SPG_HOT_SLOTS; s += 1024) hk[s] = EMPTY_KEY;
+    if (tid == 0) { fill = 0; nh = 0; }
+    __syncthreads();
+    const int64_t S = n_rows < SPG_HOT_SAMPLE ? n_rows : SPG_HOT_SAMPLE;
+    const int64_t stride = S > 0 ? n_rows / S : 1;
+    constexpr int ILP = 4;
+    for (int64_t i0 = tid; i0 < S; i0 += 1024 * ILP) {
+        long long kv[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; u++) { const int64_t i = i0 + (int64_t)u * 1024; kv[u] = i < S ? keys[i * stride] : EMPTY_KEY; }
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {
+            const long long k = kv[u];
+            if (k == EMPTY_KEY) continue;
+            unsigned int s = (unsigned int)(spg_hash(k) >> 40) & (SPG_HOT_TAB - 1);
+            for (int probes = 0; probes < 8; probes++) {  // heavy hitters arrive while the table is empty: short probes suffice
+                long long kk = *(volatile long long*)&tk[s];
+                if (kk == EMPTY_KEY) {
+                    // the table only has to hold the heavy hitters, which show up early: stop admitting keys at 50 % load
+                    if (*(volatile unsigned int*)&fill >= SPG_HOT_TAB / 2) break;
+                    kk = (long long)atomicCAS((unsigned long long*)&tk[s], (unsigned long long)EMPTY_KEY, (unsigned long long)k);
+                    if (kk == EMPTY_KEY) { atomicAdd(&fill, 1u); kk = k; }
+                }
+                if (kk == k) { atomicAdd(&tc[s], 1u); break; }
+                s = (s + 1) & (SPG_HOT_TAB - 1);
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned int T = S >= (16 << 10) ? (unsigned int)(S >> 10) : 16u;  // hot = at least 1/1024 of the sample
+    // admit candidates heaviest first (four count bands); a candidate whose two-slot bucket is taken stays an ordinary key
+    for (int band = 3; band >= 0; band--) {
+        const unsigned int lo = T << band, hi = band == 3 ? 0xffffffffu : (T << (band + 1));
+        for (int s = tid; s < SPG_HOT_TAB; s += 1024) {
+            const unsigned int c = tc[s];
+            if (c < lo || c >= hi) continue;
+            const long long k = tk[s];
+            const unsigned int hb = spg_hot_bucket(spg_hash(k));
+            unsigned long long old = atomicCAS((unsigned long long*)&hk[2 * hb], (unsigned long long)EMPTY_KEY, (unsigned long long)k);
+            if (old != (unsigned long long)EMPTY_KEY) old = atomicCAS((unsigned long long*)&hk[2 * hb + 1], (unsigned long long)EMPTY_KEY, (unsigned long long)k);
+            if (old == (unsigned long long)EMPTY_KEY) atomicAdd(&nh, 1u);
+        }
+        __syncthreads();
+    }
+    for (int s = tid; s < SPG_HOT_SLOTS; s += 1024) hot_tab[s] = hk[s];
+    if (tid == 0) *n_hot = (int)nh;
 }
 
 // K1: partition rows into owner buckets. grid = persistent (2 CTAs / SM), tiles are taken grid-stride.
@@ -730,7 +805,7 @@ __global__ void __launch_bounds__(SPG_PTHREADS, SPG_PCTAS) spg_partition_kernel(
         }
         __syncthreads();
         // reserve one run per owner; exclusive scan of the histogram by warp 0
-        if (tid < G) { unsigned int cnt = hist[tid]; gbase[tid] = cnt ? atomicAdd(&a.bucket_cnt[tid], (unsigned long long)cnt) : 0ull; }
+        if (tid < G) { unsigned int cnt = hist[tid]; gbase[tid] = cnt ? atomicAdd(&a.bucket_cnt[tid * SPG_CNT_STRIDE], (unsigned long long)cnt) : 0ull; }
         if (tid < 32) {
             unsigned int carry = 0;
             for (int base = 0; base < G; base += 32) {
@@ -792,7 +867,7 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <bool HAS_SUM, bool HAS_CNT>
+template <bool HAS_SUM, bool HAS_CNT, bool HOT = false>
 __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     long long* raw_k = (long long*)smem_raw;                                   // [NB][SPG_TILE] keys
@@ -803,7 +878,15 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
     unsigned int* hist = (unsigned int*)(mbar + 2);                            // SPG_MAX_OWNERS
     unsigned int* lbase = hist + SPG_MAX_OWNERS;                               // SPG_MAX_OWNERS + 1
     unsigned char* stage_owner = (unsigned char*)(lbase + SPG_MAX_OWNERS + 4);  // SPG_TILE
+    long long* hkeys = (long long*)(stage_owner + SPG_TILE);                   // SPG_HOT_SLOTS heavy-hitter keys ...
+    unsigned int* hlo = (unsigned int*)(hkeys + SPG_HOT_SLOTS);                // ... and this CTA's partial sums / row counts
+    unsigned int* hhi = hlo + SPG_HOT_SLOTS;
+    unsigned int* hcnt = hhi + SPG_HOT_SLOTS;
     const int G = a.n_owners, tid = threadIdx.x;
+    constexpr bool hot_on = HOT;  // separate instantiation: the uniform-key kernel carries none of this (measured: the
+                                  // same code with a run-time flag cost K1 24 % even when the flag was off)
+    if (hot_on)
+        for (int s = tid; s < SPG_HOT_SLOTS; s += SPG_TTHREADS) { hkeys[s] = a.hot_tab[s]; hlo[s] = 0; hhi[s] = 0; hcnt[s] = 0; }
     constexpr int ROWS = SPG_TILE / SPG_TTHREADS;
     const int64_t n_tiles = (a.n_rows + SPG_TILE - 1) / SPG_TILE;
     if (tid == 0) {
@@ -855,14 +938,32 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
             if (r0 + j >= a.n_rows) continue;
             const long long k = kb[j];
             if (k == EMPTY_KEY) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, k, HAS_SUM ? (unsigned long long)vb[j] : 0ull, 1ull); continue; }
-            o[r] = (int)spg_owner(spg_hash(k), G);
+            const uint64_t h = spg_hash(k);
+            if (hot_on) {  // heavy hitter: aggregate here, the row never reaches an owner bucket
+                const unsigned int hb = spg_hot_bucket(h);
+                const ulonglong2 hk2 = *reinterpret_cast<const ulonglong2*>(hkeys + 2 * hb);
+                const int hs = hk2.x == (unsigned long long)k ? (int)(2 * hb) : hk2.y == (unsigned long long)k ? (int)(2 * hb + 1) : -1;
+                if (hs >= 0) {
+                    if (HAS_SUM) {
+                        const unsigned long long v = (unsigned long long)vb[j];
+                        const unsigned int lo = (unsigned int)v;
+                        unsigned int hi = (unsigned int)(v >> 32);
+                        const unsigned int old = atomicAdd(&hlo[hs], lo);
+                        hi += (old + lo < old) ? 1u : 0u;
+                        if (hi) atomicAdd(&hhi[hs], hi);
+                    }
+                    atomicAdd(&hcnt[hs], 1u);  // rows, also when only SUM is asked for: the group has to exist
+                    continue;
+                }
+            }
+            o[r] = (int)spg_owner(h, G);
             rk[r] = atomicAdd(&hist[o[r]], 1u);
         }
         __syncthreads();
         // reserve one run per owner: the global atomic's round trip (~1 us) is kept in a register and only waited for
         // after the staging pass, which needs the local prefix sums but not the global run start
         unsigned long long my_gbase = 0;
-        if (tid >= SPG_TTHREADS - G) { int ow = tid - (SPG_TTHREADS - G); unsigned int cnt = hist[ow]; if (cnt) my_gbase = atomicAdd(&a.bucket_cnt[ow], (unsigned long long)cnt); }
+        if (tid >= SPG_TTHREADS - G) { int ow = tid - (SPG_TTHREADS - G); unsigned int cnt = hist[ow]; if (cnt) my_gbase = atomicAdd(&a.bucket_cnt[ow * SPG_CNT_STRIDE], (unsigned long long)cnt); }
         if (tid < 32) {
             unsigned int carry = 0;
             for (int base = 0; base < G; base += 32) {
@@ -898,6 +999,11 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
         }
         for (int j = tid; j < G; j += SPG_TTHREADS) hist[j] = 0;
         __syncthreads();
+    }
+    if (hot_on) {  // this CTA's heavy-hitter partials -> global table (n_hot atomics per CTA)
+        __syncthreads();
+        for (int s = tid; s < SPG_HOT_SLOTS; s += SPG_TTHREADS)
+            if (hcnt[s]) spg_direct_apply<HAS_SUM, HAS_CNT>(a, hkeys[s], (unsigned long long)hlo[s] | ((unsigned long long)hhi[s] << 32), (unsigned long long)hcnt[s]);
     }
 }
 
@@ -979,7 +1085,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
         add(s, key, val);
     };
 
-    unsigned long long n_in = a.bucket_cnt[me];
+    unsigned long long n_in = a.bucket_cnt[me * SPG_CNT_STRIDE];
     if (n_in > (unsigned long long)a.bucket_cap) n_in = (unsigned long long)a.bucket_cap;
     const longlong2* src = a.bucket + (size_t)me * a.bucket_cap;
     constexpr int U = 4;  // independent bucket loads in flight per thread
@@ -1296,7 +1402,7 @@ class GroupbyState {
         if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
         for (int b = 0; b < 2; b++) { if (stage_free[b]) cudaEventDestroy(stage_free[b]); if (stage_ready[b]) cudaEventDestroy(stage_ready[b]); }
         pinned_release(h_counters, 8 * sizeof(long long));
-        pinned_release(h_spg, 16 * sizeof(long long));
+        pinned_release(h_spg, 24 * sizeof(long long));
         for (int b = 0; b < 2; b++) if (spg_ev[b]) cudaEventDestroy(spg_ev[b]);
         for (auto& pr : prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     }
@@ -1471,19 +1577,29 @@ class GroupbyState {
                              (const void*)spg_partition_tma_kernel<false, true>};
         for (auto f : tf)
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_tma_smem()) != cudaSuccess) { cudaGetLastError(); return false; }
+        const void* hf[3] = {(const void*)spg_partition_tma_kernel<true, true, true>, (const void*)spg_partition_tma_kernel<true, false, true>,
+                             (const void*)spg_partition_tma_kernel<false, true, true>};
+        for (auto f : hf)
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_tma_smem(true)) != cudaSuccess) { cudaGetLastError(); return false; }
         { const char* e2 = getenv("B200_SPG_TMA"); spg_use_tma = !(e2 && e2[0] == '0'); }
+        if (cudaFuncSetAttribute((const void*)spg_hot_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPG_HOT_SAMPLE_SMEM) != cudaSuccess) { cudaGetLastError(); return false; }
+        { const char* e4 = getenv("B200_SPG_HOT"); spg_hot_enabled = !(e4 && e4[0] == '0'); }
+        d_hot.alloc((size_t)SPG_HOT_SLOTS * 8 + 16);
         const void* lf[3] = {(const void*)groupby_lowcard_kernel<true, true, LC_SLOTS_BIG, 2>, (const void*)groupby_lowcard_kernel<true, false, LC_SLOTS_BIG, 2>,
                              (const void*)groupby_lowcard_kernel<false, true, LC_SLOTS_BIG, 2>};
         for (auto f : lf)
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)LC_SLOTS_BIG * 20 + 64)) != cudaSuccess) { cudaGetLastError(); return false; }
         { const char* e3 = getenv("B200_LC"); lc_enabled = !(e3 && e3[0] == '0'); }
         spg_owners = sms;  // one owner (bucket + shared table) per SM
-        d_bucket_cnt.alloc((size_t)spg_owners * 8);
+        d_bucket_cnt.alloc((size_t)spg_owners * SPG_CNT_STRIDE * 8);
         spg_state = 1;
         return true;
     }
 
     bool spg_use_tma = true, lc_enabled = true, lowcard_small = false;
+    int spg_n_hot = 0;
+    bool spg_hot_enabled = true, spg_hot_sampled = false;  // heavy-hitter table: sampled once per state, at its first SPG launch
+    DevBuf d_hot;                                           // [SPG_HOT_SLOTS] keys + n_hot (int)
     int spg_passes = 1;
     static constexpr int SPG_MAX_PASSES = 24;
     // K2 passes needed for `est` groups (each pass holds spg_group_capacity() groups); 0 = too many for the SPG path
@@ -1491,7 +1607,7 @@ class GroupbyState {
         int64_t p = (est + spg_group_capacity() - 1) / spg_group_capacity();
         return p <= 1 ? 1 : (p <= SPG_MAX_PASSES ? (int)p : 0);
     }
-    static size_t spg_tma_smem() { return (size_t)SPG_TILE * (16 * SPG_TBUFS + 16 + 1) + SPG_MAX_OWNERS * 8 + 16 + (2 * SPG_MAX_OWNERS + 4) * 4 + 256; }
+    static size_t spg_tma_smem(bool hot = false) { return (size_t)SPG_TILE * (16 * SPG_TBUFS + 16 + 1) + SPG_MAX_OWNERS * 8 + 16 + (2 * SPG_MAX_OWNERS + 4) * 4 + (hot ? SPG_HOT_SLOTS * 20 : 0) + 256; }
     static size_t spg_part_smem() { return (size_t)SPG_TILE * 17 + SPG_MAX_OWNERS * 8 + (2 * SPG_MAX_OWNERS + 4) * 4 + 64; }
     bool lc_pick(int64_t est) { lowcard_small = est <= LC_SLOTS_SMALL / 4; return lc_enabled && est <= LC_SLOTS_BIG / 4; }
     // groups the shared-memory tables of all owners are expected to hold together (two-choice buckets work well up to ~70 %)
@@ -1543,7 +1659,7 @@ class GroupbyState {
 
     void consume_spg(const long long* keys, const long long* vals, int64_t n, int sum_j, int cnt_j, bool lowcard = false) {
         if (!h_spg) {
-            h_spg = (long long*)pinned_acquire(16 * sizeof(long long));
+            h_spg = (long long*)pinned_acquire(24 * sizeof(long long));  // [slot][8] counter snapshots + n_hot read-back
             for (int b = 0; b < 2; b++) B200_CUDA(cudaEventCreateWithFlags(&spg_ev[b], cudaEventDisableTiming));
         }
         double tspg0 = now();
@@ -1563,7 +1679,7 @@ class GroupbyState {
             d_bucket.ensure(device, (size_t)spg_owners * bucket_cap * 16);  // K2 of the previous launch precedes K1 of this one in stream order
             d_retry2[slot].ensure(device, ((size_t)rows + (size_t)spg_owners * spg_ns) * 32);
             t_alloc += now() - ta;
-            B200_CUDA(cudaMemsetAsync(d_bucket_cnt.p, 0, (size_t)spg_owners * 8, stream));
+            B200_CUDA(cudaMemsetAsync(d_bucket_cnt.p, 0, (size_t)spg_owners * SPG_CNT_STRIDE * 8, stream));
             SpgArgs a{};
             a.keys = keys + r0; a.vals = vals ? vals + r0 : nullptr; a.n_rows = rows; a.n_owners = spg_owners;
             a.tkeys = d_keys.as<long long>(); a.cap = cap;
@@ -1594,16 +1710,32 @@ class GroupbyState {
                 int g1 = (int)std::min<int64_t>((int64_t)sms * SPG_PCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
                 const bool tma = spg_use_tma && (((uintptr_t)a.keys & 15) == 0) && (a.vals == nullptr || ((uintptr_t)a.vals & 15) == 0);
                 int g2 = (int)std::min<int64_t>((int64_t)sms * SPG_TCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
+                if (tma && spg_hot_enabled && !spg_hot_sampled) {
+                    // once per state: count a strided sample of this launch's keys, read back how many heavy hitters it found
+                    int* d_nhot = (int*)(d_hot.as<long long>() + SPG_HOT_SLOTS);
+                    spg_hot_sample_kernel<<<1, 1024, SPG_HOT_SAMPLE_SMEM, stream>>>(a.keys, rows, d_hot.as<long long>(), d_nhot);
+                    B200_CUDA(cudaMemcpyAsync(h_spg + 16, d_nhot, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    B200_CUDA(cudaStreamSynchronize(stream));
+                    spg_n_hot = *(int*)(h_spg + 16);
+                    spg_hot_sampled = true;
+                    launches++;
+                }
+                const bool hot = tma && spg_hot_enabled && spg_n_hot > 0;
+                if (hot) { a.hot_tab = d_hot.as<long long>(); a.n_hot = (const int*)(d_hot.as<long long>() + SPG_HOT_SLOTS); }
+                const size_t tsm = spg_tma_smem(hot);
                 if (sum_j >= 0 && cnt_j >= 0) {
-                    if (tma) spg_partition_tma_kernel<true, true><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
+                    if (hot) spg_partition_tma_kernel<true, true, true><<<g2, SPG_TTHREADS, tsm, stream>>>(a);
+                    else if (tma) spg_partition_tma_kernel<true, true><<<g2, SPG_TTHREADS, tsm, stream>>>(a);
                     else spg_partition_kernel<true, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
                     spg_aggregate_kernel<true, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
                 } else if (sum_j >= 0) {
-                    if (tma) spg_partition_tma_kernel<true, false><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
+                    if (hot) spg_partition_tma_kernel<true, false, true><<<g2, SPG_TTHREADS, tsm, stream>>>(a);
+                    else if (tma) spg_partition_tma_kernel<true, false><<<g2, SPG_TTHREADS, tsm, stream>>>(a);
                     else spg_partition_kernel<true, false><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
                     spg_aggregate_kernel<true, false><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
                 } else {
-                    if (tma) spg_partition_tma_kernel<false, true><<<g2, SPG_TTHREADS, spg_tma_smem(), stream>>>(a);
+                    if (hot) spg_partition_tma_kernel<false, true, true><<<g2, SPG_TTHREADS, tsm, stream>>>(a);
+                    else if (tma) spg_partition_tma_kernel<false, true><<<g2, SPG_TTHREADS, tsm, stream>>>(a);
                     else spg_partition_kernel<false, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
                     spg_aggregate_kernel<false, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
                 }

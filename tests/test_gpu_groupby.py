@@ -213,6 +213,46 @@ def test_sm_partitioned_path_skewed_keys(gpu_lib, oracle):
     assert_frames_equal(positional(got), oracle_groupby_frame(oracle, t, 0, ["sum", "count"], [1, 1]))
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("fnames", [("sum",), ("count",), ("size", "sum")])
+def test_sm_partitioned_heavy_hitters(gpu_lib, oracle, fnames):
+    # heavy hitters are aggregated inside K1 (per-CTA shared accumulators) from a table sampled at the first launch.
+    # Two batches: the second one brings a hot key the sample has never seen (it must simply take the ordinary route),
+    # a hot key whose values cancel to zero (the group has to exist when only SUM is asked for) and values with
+    # non-zero high words (carry path of the 32-bit limb accumulators).
+    from bodo_b200.streaming.groupby import (delete_groupby_state, get_metric, groupby_build_consume_batch,
+                                             groupby_produce_output_batch, init_groupby_state)
+    from tests.helpers import table_to_device
+    rng = np.random.default_rng(5)
+    n = 2_500_000
+    def batch(hot, seed):
+        r = np.random.default_rng(seed)
+        k = r.integers(0, 150_000, n).astype(np.int64) * 13 - 77
+        u = r.random(n)
+        k[u < 0.30] = hot[0]
+        k[(u >= 0.30) & (u < 0.45)] = hot[1]
+        k[(u >= 0.45) & (u < 0.47)] = hot[2]
+        v = r.integers(-(2**40), 2**40, n).astype(np.int64)
+        v[k == hot[1]] = 0                       # sums to zero
+        v[k == hot[0]] = 2**62                   # wraps: 30 % of 2.5 M rows x 2^62
+        return pd.DataFrame({"k": k, "v": v})
+    d1, d2 = batch((123456789, -5, 42), 1), batch((987654321, -5, 123456789), 2)
+    offs, cols = [0], []
+    for f in fnames:
+        if f != "size":
+            cols.append(1)
+        offs.append(len(cols))
+    st = init_groupby_state(-1, (0,), fnames, tuple(offs), tuple(cols), expected_groups=200_000, output_batch_size=1 << 30)
+    groupby_build_consume_batch(st, table_to_device(Table.from_pandas(d1)), False, True)
+    groupby_build_consume_batch(st, table_to_device(Table.from_pandas(d2)), True, True)
+    assert get_metric(st, 8) >= 2
+    out, last = groupby_produce_output_batch(st, True)
+    got = out.to_pandas()
+    delete_groupby_state(st)
+    both = Table.from_pandas(pd.concat([d1, d2], ignore_index=True))
+    assert_frames_equal(positional(got), oracle_groupby_frame(oracle, both, 0, list(fnames), [1 if f != "size" else None for f in fnames]))
+
+
 def test_groupby_drop_duplicates_reference_fixture(gpu_lib):
     # test_groupby_drop_duplicates (bodo/tests/test_streaming/test_groupby.py:111-177): two key columns, zero functions
     df = pd.DataFrame({"A": [1, 1, 2, 4, 4, 2], "B": [1, 1, 3, 6, 6, 3]})
