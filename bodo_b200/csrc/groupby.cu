@@ -12,6 +12,7 @@
 //   * finalize compacts occupied slots and evaluates the output columns (mean_eval etc.).
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -663,6 +664,10 @@ struct SpgArgs {
                                 // estimated cardinality exceeds what the shared tables hold at once
     const long long* hot_tab;   // [SPG_HOT_SLOTS] heavy-hitter keys found by spg_hot_sample_kernel (EMPTY_KEY = free), or null
     const int* n_hot;           // number of keys in hot_tab (device memory: K1 reads it, the host never waits for it)
+    // STATIC variant (experimental, B200_SPG_STATIC=1): every (owner, K1 CTA) pair has a private segment of bucket_cap rows
+    // inside the owner's bucket, so K1 needs no global run-reservation atomics; sub_cnt[owner * n_cta + cta] = rows written
+    unsigned int* sub_cnt;
+    int n_cta;
 };
 
 // cheap in-kernel hash for owner / shared-table slot (placement inside one GPU is free to choose; the rank
@@ -867,7 +872,7 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <bool HAS_SUM, bool HAS_CNT, bool HOT = false>
+template <bool HAS_SUM, bool HAS_CNT, bool HOT = false, bool STATIC = false>
 __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     long long* raw_k = (long long*)smem_raw;                                   // [NB][SPG_TILE] keys
@@ -894,6 +899,11 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // STATIC: this CTA's private segment cursor per owner, and (cursor - local run start) for the copy-out
+    unsigned int* cursor = (unsigned int*)gbase;
+    unsigned int* cbase = cursor + SPG_MAX_OWNERS;
+    if (STATIC)
+        for (int j = tid; j < G; j += SPG_TTHREADS) cursor[j] = 0;
     for (int j = tid; j < G; j += SPG_TTHREADS) hist[j] = 0;
     __syncthreads();
     // full tiles come in through TMA; a trailing partial tile is loaded with ordinary loads
@@ -963,7 +973,7 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
         // reserve one run per owner: the global atomic's round trip (~1 us) is kept in a register and only waited for
         // after the staging pass, which needs the local prefix sums but not the global run start
         unsigned long long my_gbase = 0;
-        if (tid >= SPG_TTHREADS - G) { int ow = tid - (SPG_TTHREADS - G); unsigned int cnt = hist[ow]; if (cnt) my_gbase = atomicAdd(&a.bucket_cnt[ow * SPG_CNT_STRIDE], (unsigned long long)cnt); }
+        if (!STATIC && tid >= SPG_TTHREADS - G) { int ow = tid - (SPG_TTHREADS - G); unsigned int cnt = hist[ow]; if (cnt) my_gbase = atomicAdd(&a.bucket_cnt[ow * SPG_CNT_STRIDE], (unsigned long long)cnt); }
         if (tid < 32) {
             unsigned int carry = 0;
             for (int base = 0; base < G; base += 32) {
@@ -986,11 +996,23 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
             stage_owner[p] = (unsigned char)o[r];
         }
         // publish run start minus local start, so the copy-out computes its destination with one add
-        if (tid >= SPG_TTHREADS - G) { int ow = tid - (SPG_TTHREADS - G); gbase[ow] = my_gbase - lbase[ow]; }
+        if (STATIC) {  // no global atomic: the segment is private to this CTA
+            if (tid >= SPG_TTHREADS - G) { int ow = tid - (SPG_TTHREADS - G); cbase[ow] = cursor[ow] - lbase[ow]; cursor[ow] += hist[ow]; }
+        } else {
+            if (tid >= SPG_TTHREADS - G) { int ow = tid - (SPG_TTHREADS - G); gbase[ow] = my_gbase - lbase[ow]; }
+        }
         __syncthreads();  // raw buffer b is free from here on
         if (SPG_TBUFS == 1 && tn < n_tiles) issue(tn, 0);  // single buffer: the next tile streams in during the copy-out
         const unsigned int n_tile = lbase[G];
         for (unsigned int p = tid; p < n_tile; p += SPG_TTHREADS) {
+            if (STATIC) {
+                const unsigned int sow = stage_owner[p];
+                const unsigned int soff = cbase[sow] + p;
+                const longlong2 srow = stage[p];
+                if (soff < (unsigned int)a.bucket_cap) a.bucket[((size_t)sow * a.n_cta + blockIdx.x) * a.bucket_cap + soff] = srow;
+                else spg_direct_apply<HAS_SUM, HAS_CNT>(a, srow.x, (unsigned long long)srow.y, 1ull);
+                continue;
+            }
             unsigned int ow = stage_owner[p];
             unsigned long long off = gbase[ow] + p;
             longlong2 row = stage[p];
@@ -1000,6 +1022,9 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
         for (int j = tid; j < G; j += SPG_TTHREADS) hist[j] = 0;
         __syncthreads();
     }
+    if (STATIC)  // rows this CTA left in each owner's segment (rows beyond the segment went the direct way)
+        for (int j = tid; j < G; j += SPG_TTHREADS)
+            a.sub_cnt[(size_t)j * a.n_cta + blockIdx.x] = cursor[j] < (unsigned int)a.bucket_cap ? cursor[j] : (unsigned int)a.bucket_cap;
     if (hot_on) {  // this CTA's heavy-hitter partials -> global table (n_hot atomics per CTA)
         __syncthreads();
         for (int s = tid; s < SPG_HOT_SLOTS; s += SPG_TTHREADS)
@@ -1017,7 +1042,7 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
 // (~2 % at this load: linear-probing stash behind the buckets), a full stash (direct global path), a non-zero high word
 // of the sum — is parked and handled once per iteration behind the hot path.  Two racing inserts may put one key into
 // both of its buckets: harmless, both partial sums are flushed into the same global group.
-template <bool HAS_SUM, bool HAS_CNT>
+template <bool HAS_SUM, bool HAS_CNT, bool STATIC = false>
 __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NS = a.ns, NT = a.ns + SPG_STASH, tid = threadIdx.x, me = blockIdx.x;  // NS bucket slots + stash
@@ -1085,18 +1110,24 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
         add(s, key, val);
     };
 
-    unsigned long long n_in = a.bucket_cnt[me * SPG_CNT_STRIDE];
+    unsigned long long n_in = STATIC ? 0ull : a.bucket_cnt[me * SPG_CNT_STRIDE];
     if (n_in > (unsigned long long)a.bucket_cap) n_in = (unsigned long long)a.bucket_cap;
+    unsigned int* seg_cnt = scnt + NT + 4;  // STATIC: rows in each K1 CTA's segment of this owner's bucket (behind the table)
+    if (STATIC) {
+        for (int i = tid; i < a.n_cta; i += SPG_THREADS) seg_cnt[i] = a.sub_cnt[(size_t)me * a.n_cta + i];
+        __syncthreads();
+    }
     const longlong2* src = a.bucket + (size_t)me * a.bucket_cap;
     constexpr int U = 4;  // independent bucket loads in flight per thread
-    auto process = [&](unsigned long long base, unsigned int pass, auto full_tag) {
+    // rows of this thread: rsrc[first + u * stride], u = 0..U-1, valid while < limit
+    auto process = [&](const longlong2* rsrc, unsigned long long first, unsigned long long stride, unsigned long long limit, unsigned int pass, auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;  // FULL: all U rows of every thread are in range (no padding checks)
         longlong2 row[U];
         int sl[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            unsigned long long p = base + tid + (unsigned long long)u * SPG_THREADS;
-            row[u] = (FULL || p < n_in) ? __ldcs(src + p) : make_longlong2(EMPTY_KEY, 0);
+            unsigned long long p = first + (unsigned long long)u * stride;
+            row[u] = (FULL || p < limit) ? __ldcs(rsrc + p) : make_longlong2(EMPTY_KEY, 0);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {  // hot lookups: branch-free
@@ -1127,8 +1158,23 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     for (unsigned int pass = 0; pass < NP; pass++) {
         for (int s = tid; s < NT; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0x80000000u; scnt[s] = 0; }
         __syncthreads();
-        for (unsigned long long base = 0; base < n_full; base += step) process(base, pass, std::true_type{});
-        if (n_full < n_in) process(n_full, pass, std::false_type{});
+        if (STATIC) {
+            // every warp streams whole 128-row chunks of the per-(K1 CTA) segments of this owner's bucket: no CTA-wide
+            // iteration, the warps drift apart freely
+            const unsigned int NC = (unsigned int)a.n_cta, C = (unsigned int)a.bucket_cap, CH = (C + 32 * U - 1) / (32 * U);
+            const unsigned int lane = (unsigned int)tid & 31u;
+            for (unsigned int item = (unsigned int)tid >> 5; item < NC * CH; item += SPG_THREADS / 32) {
+                const unsigned int sub = item / CH, r0 = (item - sub * CH) * (32 * U);
+                const unsigned int n = seg_cnt[sub];
+                if (r0 >= n) continue;
+                const longlong2* seg = a.bucket + ((size_t)me * NC + sub) * C + r0;
+                if (r0 + 32 * U <= n) process(seg, lane, 32ull, (unsigned long long)(n - r0), pass, std::true_type{});
+                else process(seg, lane, 32ull, (unsigned long long)(n - r0), pass, std::false_type{});
+            }
+        } else {
+            for (unsigned long long base = 0; base < n_full; base += step) process(src, base + tid, (unsigned long long)SPG_THREADS, n_in, pass, std::true_type{});
+            if (n_full < n_in) process(src, n_full + tid, (unsigned long long)SPG_THREADS, n_in, pass, std::false_type{});
+        }
         __syncthreads();
         // flush the shared table into the state's global table
         for (int s = tid; s < NT; s += SPG_THREADS) {
@@ -1581,6 +1627,21 @@ class GroupbyState {
                              (const void*)spg_partition_tma_kernel<false, true, true>};
         for (auto f : hf)
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_tma_smem(true)) != cudaSuccess) { cudaGetLastError(); return false; }
+        {   // experimental STATIC variant (private (owner, CTA) segments instead of run-reservation atomics)
+            const char* e5 = getenv("B200_SPG_STATIC");
+            spg_static = e5 && e5[0] == '1';
+            if (spg_static) {
+                const void* sf[6] = {(const void*)spg_partition_tma_kernel<true, true, false, true>, (const void*)spg_partition_tma_kernel<true, false, false, true>,
+                                     (const void*)spg_partition_tma_kernel<false, true, false, true>, (const void*)spg_partition_tma_kernel<true, true, true, true>,
+                                     (const void*)spg_partition_tma_kernel<true, false, true, true>, (const void*)spg_partition_tma_kernel<false, true, true, true>};
+                for (auto f : sf)
+                    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_tma_smem(true)) != cudaSuccess) { cudaGetLastError(); return false; }
+                const void* af[3] = {(const void*)spg_aggregate_kernel<true, true, true>, (const void*)spg_aggregate_kernel<true, false, true>,
+                                     (const void*)spg_aggregate_kernel<false, true, true>};
+                for (auto f : af)
+                    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_smem) != cudaSuccess) { cudaGetLastError(); return false; }
+            }
+        }
         { const char* e2 = getenv("B200_SPG_TMA"); spg_use_tma = !(e2 && e2[0] == '0'); }
         if (cudaFuncSetAttribute((const void*)spg_hot_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPG_HOT_SAMPLE_SMEM) != cudaSuccess) { cudaGetLastError(); return false; }
         { const char* e4 = getenv("B200_SPG_HOT"); spg_hot_enabled = !(e4 && e4[0] == '0'); }
@@ -1598,6 +1659,9 @@ class GroupbyState {
 
     bool spg_use_tma = true, lc_enabled = true, lowcard_small = false;
     int spg_n_hot = 0;
+    bool spg_static = false;   // B200_SPG_STATIC=1
+    PooledBuf d_sub_cnt;       // STATIC: [owners][K1 CTAs] rows per segment
+    static constexpr int SPG_STATIC_CNT_SLOTS = 128;  // table slots given up for the segment counters (512 x 4 B)
     bool spg_hot_enabled = true, spg_hot_sampled = false;  // heavy-hitter table: sampled once per state, at its first SPG launch
     DevBuf d_hot;                                           // [SPG_HOT_SLOTS] keys + n_hot (int)
     int spg_passes = 1;
@@ -1675,8 +1739,18 @@ class GroupbyState {
             // uniform keys put rows / owners rows in every bucket (sd = sqrt of that); 12.5 % + 4096 rows head room,
             // anything beyond (skew) takes the direct path inside K1
             int64_t bucket_cap = (rows / spg_owners) + (rows / spg_owners) / 8 + 4096;
+            const int64_t n_tiles = (rows + SPG_TILE - 1) / SPG_TILE;
+            const int g2s = (int)std::min<int64_t>((int64_t)sms * SPG_TCTAS, n_tiles);  // K1 grid of the TMA variants
+            const bool use_static = spg_static && !lowcard && spg_use_tma && g2s <= 4 * SPG_STATIC_CNT_SLOTS &&
+                                    (((uintptr_t)(keys + r0)) & 15) == 0 && (vals == nullptr || (((uintptr_t)(vals + r0)) & 15) == 0);
+            if (use_static) {
+                // segment of one (owner, K1 CTA) pair: that CTA's share of the rows / owners, + 6 sigma + slack, 128-byte multiple
+                const double mean = (double)((n_tiles + g2s - 1) / g2s) * SPG_TILE / spg_owners;
+                bucket_cap = ((int64_t)(mean + 6.0 * std::sqrt(mean) + 64.0) + 7) & ~7ll;
+            }
             double ta = now();
-            d_bucket.ensure(device, (size_t)spg_owners * bucket_cap * 16);  // K2 of the previous launch precedes K1 of this one in stream order
+            d_bucket.ensure(device, (size_t)spg_owners * (use_static ? (size_t)g2s : 1) * bucket_cap * 16);  // K2 of the previous launch precedes K1 of this one in stream order
+            if (use_static) d_sub_cnt.ensure(device, (size_t)spg_owners * g2s * 4);
             d_retry2[slot].ensure(device, ((size_t)rows + (size_t)spg_owners * spg_ns) * 32);
             t_alloc += now() - ta;
             B200_CUDA(cudaMemsetAsync(d_bucket_cnt.p, 0, (size_t)spg_owners * SPG_CNT_STRIDE * 8, stream));
@@ -1723,7 +1797,20 @@ class GroupbyState {
                 const bool hot = tma && spg_hot_enabled && spg_n_hot > 0;
                 if (hot) { a.hot_tab = d_hot.as<long long>(); a.n_hot = (const int*)(d_hot.as<long long>() + SPG_HOT_SLOTS); }
                 const size_t tsm = spg_tma_smem(hot);
-                if (sum_j >= 0 && cnt_j >= 0) {
+                if (use_static) {
+                    a.sub_cnt = d_sub_cnt.as<unsigned int>(); a.n_cta = g2; a.ns = spg_ns - SPG_STATIC_CNT_SLOTS;
+                    const size_t ssm = spg_tma_smem(true);
+#define B200_SPG_STATIC_LAUNCH(S, C)                                                                                      \
+    do {                                                                                                                  \
+        if (hot) spg_partition_tma_kernel<S, C, true, true><<<g2, SPG_TTHREADS, ssm, stream>>>(a);                        \
+        else spg_partition_tma_kernel<S, C, false, true><<<g2, SPG_TTHREADS, ssm, stream>>>(a);                           \
+        spg_aggregate_kernel<S, C, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);                               \
+    } while (0)
+                    if (sum_j >= 0 && cnt_j >= 0) B200_SPG_STATIC_LAUNCH(true, true);
+                    else if (sum_j >= 0) B200_SPG_STATIC_LAUNCH(true, false);
+                    else B200_SPG_STATIC_LAUNCH(false, true);
+#undef B200_SPG_STATIC_LAUNCH
+                } else if (sum_j >= 0 && cnt_j >= 0) {
                     if (hot) spg_partition_tma_kernel<true, true, true><<<g2, SPG_TTHREADS, tsm, stream>>>(a);
                     else if (tma) spg_partition_tma_kernel<true, true><<<g2, SPG_TTHREADS, tsm, stream>>>(a);
                     else spg_partition_kernel<true, true><<<g1, SPG_PTHREADS, spg_part_smem(), stream>>>(a);
