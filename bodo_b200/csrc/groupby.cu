@@ -767,7 +767,8 @@ __global__ void __launch_bounds__(1024, 1) spg_hot_sample_kernel(const long long
     if (tid == 0) *n_hot = (int)nh;
 }
 
-// K1: partition rows into owner buckets. grid = persistent (2 CTAs / SM), tiles are taken grid-stride.
+// K1 (plain-load fallback, used when the inputs are not 16-byte aligned or B200_SPG_TMA=0): partition rows into owner
+// buckets. grid = persistent (SPG_PCTAS CTAs / SM), tiles are taken grid-stride.
 template <bool HAS_SUM, bool HAS_CNT>
 __global__ void __launch_bounds__(SPG_PTHREADS, SPG_PCTAS) spg_partition_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
