@@ -2,6 +2,7 @@
 bodo/pandas/physical/operator.h:46-50,247-458; aggregate.h:65-365; join.h:58-744; _pipeline.cpp:389-466).
 
     OperatorResult.{NEED_MORE_INPUT, HAVE_MORE_OUTPUT, FINISHED}
+    PhysicalReadPandas / PhysicalReadArrow / PhysicalReadParquet : sources (batches of host columns)
     PhysicalAggregate : sink of one pipeline (ConsumeBatch) and source of the next (ProduceBatch)
     PhysicalJoin      : sink for the build side, ProcessBatch for the probe side
     Pipeline          : while not finished: batch = source.ProduceBatch(); ... sink.ConsumeBatch(batch)
@@ -43,6 +44,54 @@ class PhysicalReadPandas:
         batch = self.table.slice(self.cur, self.cur + self.batch_size)
         self.cur += self.batch_size
         return batch, (OperatorResult.FINISHED if self.cur >= n else OperatorResult.HAVE_MORE_OUTPUT)
+
+
+class PhysicalReadArrow:
+    """Source over an in-memory pyarrow Table: batch_size-row zero-copy slices (the Arrow half of
+    PhysicalReadPandas, read_pandas.h:13-120: the reference converts every pandas slice to Arrow first)."""
+
+    def __init__(self, table, batch_size: int = STREAMING_BATCH_SIZE):
+        self.arrow = table.combine_chunks()
+        self.batch_size = batch_size
+        self.cur = 0
+
+    def ProduceBatch(self):
+        n = self.arrow.num_rows
+        batch = Table.from_arrow(self.arrow.slice(self.cur, self.batch_size))
+        self.cur += self.batch_size
+        return batch, (OperatorResult.FINISHED if self.cur >= n else OperatorResult.HAVE_MORE_OUTPUT)
+
+
+class PhysicalReadParquet:
+    """Source over a Parquet file or dataset directory (host side of physical/read_parquet.h:31-210 — the reference
+    streams Arrow record batches out of its ParquetReader; here pyarrow's reader produces them).  Only the selected
+    columns are decoded; every batch has at most batch_size rows; an empty dataset yields one empty, FINISHED batch."""
+
+    def __init__(self, path: str, columns: Sequence[str] | None = None, batch_size: int = STREAMING_BATCH_SIZE):
+        import pyarrow.dataset as ds
+
+        self.dataset = ds.dataset(path, format="parquet")
+        self.columns = list(columns) if columns is not None else None
+        self.schema = self.dataset.schema
+        self._it = iter(self.dataset.to_batches(columns=self.columns, batch_size=batch_size))
+        self._next = self._pull()
+
+    def _pull(self):
+        for rb in self._it:
+            if rb.num_rows:
+                return rb
+        return None
+
+    def ProduceBatch(self):
+        import pyarrow as pa
+
+        cur = self._next
+        if cur is None:  # empty dataset
+            names = self.columns if self.columns is not None else list(self.schema.names)
+            empty = pa.table({n: pa.array([], type=self.schema.field(n).type) for n in names})
+            return Table.from_arrow(empty), OperatorResult.FINISHED
+        self._next = self._pull()
+        return Table.from_arrow(cur), (OperatorResult.FINISHED if self._next is None else OperatorResult.HAVE_MORE_OUTPUT)
 
 
 class PhysicalAggregate:
@@ -141,6 +190,27 @@ def groupby_agg(df, by, aggs: Sequence[tuple], dropna: bool = True, batch_size: 
     agg_spec = [(f, None if f == "size" or c is None else used.index(c)) for _, c, f in aggs]
     op = PhysicalAggregate(key_inds, agg_spec, dropna=dropna, **kw)
     run_pipeline(PhysicalReadPandas(sub, batch_size), [], op)
+    coll = ResultCollector()
+    run_pipeline(op, [], coll)
+    op.Finalize()
+    out = coll.result()
+    out.columns = by + [name for name, _, _ in aggs]
+    return out
+
+
+def groupby_agg_parquet(path: str, by, aggs: Sequence[tuple], dropna: bool = True, batch_size: int = STREAMING_BATCH_SIZE, **kw):
+    """bodo.pandas.read_parquet(path).groupby(by, as_index=False, dropna=dropna).agg(...): PhysicalReadParquet feeding
+    PhysicalAggregate.  Only the key and aggregated columns are decoded (column pruning, as the reference's planner does
+    for ReadParquet under an aggregate).  Same `aggs` format and result shape as groupby_agg."""
+    by = [by] if isinstance(by, str) else list(by)
+    used = list(by)
+    for _, c, _ in aggs:
+        if c is not None and c not in used:
+            used.append(c)
+    key_inds = [used.index(k) for k in by]
+    agg_spec = [(f, None if f == "size" or c is None else used.index(c)) for _, c, f in aggs]
+    op = PhysicalAggregate(key_inds, agg_spec, dropna=dropna, **kw)
+    run_pipeline(PhysicalReadParquet(path, used, batch_size), [], op)
     coll = ResultCollector()
     run_pipeline(op, [], coll)
     op.Finalize()

@@ -286,8 +286,22 @@ def column_from_arrow(a) -> Column:
     if isinstance(a, pa.ChunkedArray):
         a = a.combine_chunks()
     t = a.type
+    # temporal columns travel as their integer storage with the reference's dtype code (Bodo_CTypes DATE = int32 days,
+    # DATETIME / TIMEDELTA = int64 nanoseconds, bodo/libs/_bodo_common.h:331-359); other units are brought to ns first
+    c_type = None
+    if pa.types.is_date32(t):
+        a, c_type = a.view(pa.int32()), CTypes.DATE
+    elif pa.types.is_timestamp(t) or pa.types.is_duration(t):
+        is_ts = pa.types.is_timestamp(t)
+        if t.unit != "ns":
+            a = a.cast(pa.timestamp("ns", tz=t.tz) if is_ts else pa.duration("ns"))
+        a, c_type = a.view(pa.int64()), (CTypes.DATETIME if is_ts else CTypes.TIMEDELTA)
+    elif pa.types.is_date64(t):
+        a, c_type = a.cast(pa.timestamp("ns")).view(pa.int64()), CTypes.DATETIME
+    t = a.type
     if not (pa.types.is_integer(t) or pa.types.is_floating(t)):
-        raise TypeError(f"bodo_b200: unsupported Arrow type {t}")
+        raise TypeError(f"bodo_b200: unsupported Arrow type {t} (fixed-width numeric, date and timestamp columns only; "
+                        "strings are a 'next' row, SURVEY.md §8f)")
     np_dt = np.dtype(t.to_pandas_dtype())
     bufs = a.buffers()
     n = len(a)
@@ -300,7 +314,7 @@ def column_from_arrow(a) -> Column:
     if bufs[0] is not None and a.null_count > 0:
         validity = np.frombuffer(bufs[0], dtype=np.uint8)[off // 8 : off // 8 + (n + 7) // 8]
     arr_type = ArrTypes.NULLABLE_INT_BOOL  # Arrow columns are nullable by construction
-    return Column(np.ascontiguousarray(data), validity, ctype_of(np_dt), arr_type, n)
+    return Column(np.ascontiguousarray(data), validity, c_type if c_type is not None else ctype_of(np_dt), arr_type, n)
 
 
 def column_to_pandas(c: Column, stream: int = 0):
@@ -311,7 +325,12 @@ def column_to_pandas(c: Column, stream: int = 0):
         vals = vals.view("datetime64[ns]")
     elif c.c_type == CTypes.TIMEDELTA:
         vals = vals.view("timedelta64[ns]")
+    elif c.c_type == CTypes.DATE:
+        vals = vals.astype("int64").view("datetime64[D]")
     mask = c.valid_mask_numpy(stream)
+    if vals.dtype.kind in "Mm" and mask is not None and not mask.all():
+        vals = vals.copy()
+        vals[~mask] = np.datetime64("NaT") if vals.dtype.kind == "M" else np.timedelta64("NaT")
     if c.arr_type == ArrTypes.NULLABLE_INT_BOOL and vals.dtype.kind in "iuf":
         name = {"i": "Int", "u": "UInt", "f": "Float"}[vals.dtype.kind] + str(vals.dtype.itemsize * 8)
         m = ~mask if mask is not None else np.zeros(len(vals), dtype=bool)

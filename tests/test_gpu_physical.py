@@ -6,7 +6,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from bodo_b200.physical import groupby_agg, merge
+from bodo_b200.physical import groupby_agg, groupby_agg_parquet, merge
 
 pytestmark = pytest.mark.gpu
 
@@ -51,3 +51,21 @@ def test_merge_vs_pandas(gpu_lib, how):
     exp = left.merge(right, left_on="a", right_on="b", how=how)[["b", "rv", "a", "lv"]]
     assert len(got) == len(exp)
     np.testing.assert_allclose(_sorted(got).to_numpy(), _sorted(exp).to_numpy(), rtol=0, atol=0, equal_nan=True)
+
+
+def test_groupby_from_parquet_vs_pandas(gpu_lib, tmp_path):
+    # read_parquet -> groupby -> agg (the shape of bodo/tests/test_df_lib/test_gpu/test_gpu_end_to_end.py:68-110):
+    # PhysicalReadParquet streams Arrow record batches (nullable columns, several row groups) into PhysicalAggregate
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+
+    rng = np.random.default_rng(12)
+    n = 50_000
+    x = rng.integers(-1000, 1000, n).astype("float64")
+    x[rng.random(n) < 0.05] = np.nan
+    df = pd.DataFrame({"k": rng.integers(0, 300, n), "x": pd.array(x).astype("Int64"), "y": rng.random(n), "unused": rng.random(n)})
+    path = str(tmp_path / "t.parquet")
+    pq.write_table(pa.Table.from_pandas(df, preserve_index=False), path, row_group_size=7000)
+    got = groupby_agg_parquet(path, "k", [("sx", "x", "sum"), ("cx", "x", "count"), ("my", "y", "mean"), ("n", None, "size")], batch_size=4096)
+    exp = df.groupby("k", as_index=False).agg(sx=("x", "sum"), cx=("x", "count"), my=("y", "mean"), n=("y", "size"))
+    np.testing.assert_allclose(_sorted(got).to_numpy(), _sorted(exp).to_numpy(), rtol=1e-5, atol=1e-8)
