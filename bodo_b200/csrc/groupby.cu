@@ -1054,7 +1054,12 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     unsigned int* slo = (unsigned int*)(skeys + NT);  // NT x 4
     unsigned int* scnt = slo + NT;
     const unsigned int NB = (unsigned int)NS / 2;
+#ifdef SPG_K2_NP1  // scratch/spg_harness experiment: single-pass kernel, the per-row pass test is compiled out
+    constexpr unsigned int NP = 1;
+    const unsigned int GP = (unsigned int)gridDim.x;
+#else
     const unsigned int NP = (unsigned int)a.n_pass, GP = (unsigned int)gridDim.x * NP;
+#endif
 
     auto buckets = [&](long long key, unsigned int& b1, unsigned int& b2) {
         const uint64_t h = spg_hash(key);
@@ -1173,8 +1178,53 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
                 else process(seg, lane, 32ull, (unsigned long long)(n - r0), pass, std::false_type{});
             }
         } else {
+#ifdef SPG_K2_PIPE
+            // scratch/spg_harness experiment: software pipeline — the next UP rows of every thread are in flight while the
+            // current UP rows are aggregated (same register budget as U = 4 rows loaded at once)
+            constexpr int UP = 2;
+            const unsigned long long pstep = (unsigned long long)UP * SPG_THREADS;
+            longlong2 cur[UP], nxt[UP];
+#pragma unroll
+            for (int u = 0; u < UP; u++) {
+                const unsigned long long p = tid + (unsigned long long)u * SPG_THREADS;
+                cur[u] = p < n_in ? __ldcs(src + p) : make_longlong2(EMPTY_KEY, 0);
+            }
+            for (unsigned long long base = 0; base < n_in; base += pstep) {
+#pragma unroll
+                for (int u = 0; u < UP; u++) {
+                    const unsigned long long p = base + pstep + tid + (unsigned long long)u * SPG_THREADS;
+                    nxt[u] = p < n_in ? __ldcs(src + p) : make_longlong2(EMPTY_KEY, 0);
+                }
+                int sl[UP];
+#pragma unroll
+                for (int u = 0; u < UP; u++) {
+                    unsigned int b1, b2;
+                    buckets(cur[u].x, b1, b2);
+                    const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(skeys + 2 * b1);
+                    const ulonglong2 k2 = *reinterpret_cast<const ulonglong2*>(skeys + 2 * b2);
+                    const unsigned long long uk = (unsigned long long)cur[u].x;
+                    sl[u] = k1.x == uk ? (int)(2 * b1) : k1.y == uk ? (int)(2 * b1 + 1) : k2.x == uk ? (int)(2 * b2) : k2.y == uk ? (int)(2 * b2 + 1) : -1;
+                    if (cur[u].x == EMPTY_KEY) sl[u] = -2;
+                    if (NP > 1 && __umulhi((unsigned int)(spg_hash(cur[u].x) >> 32), GP) - (unsigned int)me * NP != pass) sl[u] = -2;
+                }
+                long long pk = 0, pv = 0;
+                bool parked = false;
+#pragma unroll
+                for (int u = 0; u < UP; u++) {
+                    if (sl[u] >= 0) add(sl[u], cur[u].x, cur[u].y);
+                    else if (sl[u] == -1) {
+                        if (!parked) { pk = cur[u].x; pv = cur[u].y; parked = true; }
+                        else slow_upsert(cur[u].x, cur[u].y);
+                    }
+                }
+                if (parked) slow_upsert(pk, pv);
+#pragma unroll
+                for (int u = 0; u < UP; u++) cur[u] = nxt[u];
+            }
+#else
             for (unsigned long long base = 0; base < n_full; base += step) process(src, base + tid, (unsigned long long)SPG_THREADS, n_in, pass, std::true_type{});
             if (n_full < n_in) process(src, n_full + tid, (unsigned long long)SPG_THREADS, n_in, pass, std::false_type{});
+#endif
         }
         __syncthreads();
         // flush the shared table into the state's global table

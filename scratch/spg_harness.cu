@@ -126,3 +126,6 @@ int main(int argc, char** argv) {
            rows * 16.0 / ((m1 + m2) * 1e-3) / 6574.8e9, hc[0], hc[1], ok ? "ok" : "MISMATCH");
     return ok ? 0 : 3;
 }
+// Variants (compile-time, harness builds only; the library never defines these):
+//   -DSPG_K2_NP1   single-pass K2, per-row pass test compiled out
+//   -DSPG_K2_PIPE  K2 with a 2 + 2 software pipeline of the bucket loads
