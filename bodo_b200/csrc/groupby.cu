@@ -875,8 +875,8 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
 
 template <bool HAS_SUM, bool HAS_CNT, bool HOT = false, bool STATIC = false>
 __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_kernel(const __grid_constant__ SpgArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    long long* raw_k = (long long*)smem_raw;                                   // [NB][SPG_TILE] keys
+    extern __shared__ __align__(128) unsigned char smem_tma_raw[];  // own name: the other kernels declare smem_raw with 16-byte alignment
+    long long* raw_k = (long long*)smem_tma_raw;                                   // [NB][SPG_TILE] keys
     long long* raw_v = raw_k + SPG_TBUFS * SPG_TILE;                           // [NB][SPG_TILE] values
     longlong2* stage = (longlong2*)(raw_v + SPG_TBUFS * SPG_TILE);             // SPG_TILE x 16
     unsigned long long* gbase = (unsigned long long*)(stage + SPG_TILE);      // SPG_MAX_OWNERS x 8
