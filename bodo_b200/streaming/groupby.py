@@ -14,9 +14,7 @@ reference's MPI shuffle (streaming/_shuffle.cpp:687-804).
 
 from __future__ import annotations
 
-from typing import Sequence
 
-import numpy as np
 
 from .. import _lib
 from .._lib import ffi

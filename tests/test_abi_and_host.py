@@ -9,7 +9,7 @@ import pandas as pd
 import pytest
 
 from bodo_b200 import B200Error, _lib
-from bodo_b200.table import ArrTypes, Column, CTable, CTypes, Table
+from bodo_b200.table import ArrTypes, CTable, CTypes, Table
 
 
 def test_library_exports_every_declared_symbol():
