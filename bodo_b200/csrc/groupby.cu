@@ -1043,7 +1043,7 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
 // (~2 % at this load: linear-probing stash behind the buckets), a full stash (direct global path), a non-zero high word
 // of the sum — is parked and handled once per iteration behind the hot path.  Two racing inserts may put one key into
 // both of its buckets: harmless, both partial sums are flushed into the same global group.
-template <bool HAS_SUM, bool HAS_CNT, bool STATIC = false>
+template <bool HAS_SUM, bool HAS_CNT, bool STATIC = false, bool INPUT = false>
 __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NS = a.ns, NT = a.ns + SPG_STASH, tid = threadIdx.x, me = blockIdx.x;  // NS bucket slots + stash
@@ -1116,7 +1116,14 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
         add(s, key, val);
     };
 
-    unsigned long long n_in = STATIC ? 0ull : a.bucket_cnt[me * SPG_CNT_STRIDE];
+    // INPUT (one-pass variant for a few thousand groups, experimental, B200_SPG_ONEPASS=1): no K1 and no owner buckets —
+    // every CTA aggregates a contiguous slice of the INPUT columns in its own table (which then holds all groups).
+    const int64_t in_per = INPUT ? ((((a.n_rows + gridDim.x - 1) / gridDim.x) + 1) & ~1ll) : 0;  // even: 16-byte loads
+    const int64_t in_lo = (int64_t)me * in_per;
+    const int64_t in_n = INPUT ? (a.n_rows - in_lo < 0 ? 0 : (a.n_rows - in_lo < in_per ? a.n_rows - in_lo : in_per)) : 0;
+    const long long* ikeys = INPUT ? a.keys + in_lo : nullptr;
+    const long long* ivals = (INPUT && HAS_SUM) ? a.vals + in_lo : nullptr;
+    unsigned long long n_in = (STATIC || INPUT) ? 0ull : a.bucket_cnt[me * SPG_CNT_STRIDE];
     if (n_in > (unsigned long long)a.bucket_cap) n_in = (unsigned long long)a.bucket_cap;
     unsigned int* seg_cnt = scnt + NT + 4;  // STATIC: rows in each K1 CTA's segment of this owner's bucket (behind the table)
     if (STATIC) {
@@ -1130,10 +1137,33 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
         constexpr bool FULL = decltype(full_tag)::value;  // FULL: all U rows of every thread are in range (no padding checks)
         longlong2 row[U];
         int sl[U];
+        if (INPUT) {
+            // units of two adjacent rows (first / stride count units, limit counts rows): 16-byte loads from both columns;
+            // a real row whose key equals the free-slot marker goes the direct way here (K1 does that for the bucket path)
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            unsigned long long p = first + (unsigned long long)u * stride;
-            row[u] = (FULL || p < limit) ? __ldcs(rsrc + p) : make_longlong2(EMPTY_KEY, 0);
+            for (int j = 0; j < U / 2; j++) {
+                const unsigned long long r = 2 * (first + (unsigned long long)j * stride);
+                row[2 * j] = row[2 * j + 1] = make_longlong2(EMPTY_KEY, 0);
+                if (FULL || r + 1 < limit) {
+                    const longlong2 kk = __ldcs(reinterpret_cast<const longlong2*>(ikeys + r));
+                    longlong2 vv = make_longlong2(0, 0);
+                    if (HAS_SUM) vv = __ldcs(reinterpret_cast<const longlong2*>(ivals + r));
+                    row[2 * j] = make_longlong2(kk.x, vv.x);
+                    row[2 * j + 1] = make_longlong2(kk.y, vv.y);
+                    if (kk.x == EMPTY_KEY) spg_direct_apply<HAS_SUM, HAS_CNT>(a, kk.x, (unsigned long long)vv.x, 1ull);
+                    if (kk.y == EMPTY_KEY) spg_direct_apply<HAS_SUM, HAS_CNT>(a, kk.y, (unsigned long long)vv.y, 1ull);
+                } else if (r < limit) {
+                    const long long k0 = ikeys[r], v0 = HAS_SUM ? ivals[r] : 0;
+                    row[2 * j] = make_longlong2(k0, v0);
+                    if (k0 == EMPTY_KEY) spg_direct_apply<HAS_SUM, HAS_CNT>(a, k0, (unsigned long long)v0, 1ull);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                unsigned long long p = first + (unsigned long long)u * stride;
+                row[u] = (FULL || p < limit) ? __ldcs(rsrc + p) : make_longlong2(EMPTY_KEY, 0);
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {  // hot lookups: branch-free
@@ -1143,7 +1173,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
             const ulonglong2 k2 = *reinterpret_cast<const ulonglong2*>(skeys + 2 * b2);
             const unsigned long long uk = (unsigned long long)row[u].x;
             sl[u] = k1.x == uk ? (int)(2 * b1) : k1.y == uk ? (int)(2 * b1 + 1) : k2.x == uk ? (int)(2 * b2) : k2.y == uk ? (int)(2 * b2 + 1) : -1;
-            if (!FULL && row[u].x == EMPTY_KEY) sl[u] = -2;  // padding lane
+            if ((!FULL || INPUT) && row[u].x == EMPTY_KEY) sl[u] = -2;  // padding lane (INPUT: also marker-key rows, handled above)
             // multi-pass: owner = mulhi(hash_hi, G) = mulhi(hash_hi, G * NP) / NP; this pass keeps sub-range `pass` only
             if (NP > 1 && __umulhi((unsigned int)(spg_hash(row[u].x) >> 32), GP) - (unsigned int)me * NP != pass) sl[u] = -2;
         }
@@ -1164,7 +1194,12 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     for (unsigned int pass = 0; pass < NP; pass++) {
         for (int s = tid; s < NT; s += SPG_THREADS) { skeys[s] = EMPTY_KEY; slo[s] = 0x80000000u; scnt[s] = 0; }
         __syncthreads();
-        if (STATIC) {
+        if constexpr (INPUT) {
+            const unsigned long long ustep = (unsigned long long)(U / 2) * SPG_THREADS;          // units per CTA iteration
+            const unsigned long long full_units = (unsigned long long)in_n / (2 * ustep) * ustep;  // iterations with every row in range
+            for (unsigned long long ub = 0; ub < full_units; ub += ustep) process(nullptr, ub + tid, (unsigned long long)SPG_THREADS, (unsigned long long)in_n, pass, std::true_type{});
+            for (unsigned long long ub = full_units; 2 * ub < (unsigned long long)in_n; ub += ustep) process(nullptr, ub + tid, (unsigned long long)SPG_THREADS, (unsigned long long)in_n, pass, std::false_type{});
+        } else if (STATIC) {
             // every warp streams whole 128-row chunks of the per-(K1 CTA) segments of this owner's bucket: no CTA-wide
             // iteration, the warps drift apart freely
             const unsigned int NC = (unsigned int)a.n_cta, C = (unsigned int)a.bucket_cap, CH = (C + 32 * U - 1) / (32 * U);
@@ -1678,6 +1713,16 @@ class GroupbyState {
                              (const void*)spg_partition_tma_kernel<false, true, true>};
         for (auto f : hf)
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_tma_smem(true)) != cudaSuccess) { cudaGetLastError(); return false; }
+        {   // experimental one-pass variant for a few thousand groups (K2's table over the input columns, no K1)
+            const char* e6 = getenv("B200_SPG_ONEPASS");
+            spg_onepass = e6 && e6[0] == '1';
+            if (spg_onepass) {
+                const void* of[3] = {(const void*)spg_aggregate_kernel<true, true, false, true>, (const void*)spg_aggregate_kernel<true, false, false, true>,
+                                     (const void*)spg_aggregate_kernel<false, true, false, true>};
+                for (auto f : of)
+                    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spg_smem) != cudaSuccess) { cudaGetLastError(); return false; }
+            }
+        }
         {   // experimental STATIC variant (private (owner, CTA) segments instead of run-reservation atomics)
             const char* e5 = getenv("B200_SPG_STATIC");
             spg_static = e5 && e5[0] == '1';
@@ -1711,6 +1756,9 @@ class GroupbyState {
     bool spg_use_tma = true, lc_enabled = true, lowcard_small = false;
     int spg_n_hot = 0;
     bool spg_static = false;   // B200_SPG_STATIC=1
+    bool spg_onepass = false;  // B200_SPG_ONEPASS=1
+    // groups one CTA's table takes at ~45 % load: the one-pass variant keeps ALL groups in every CTA
+    int64_t spg_onepass_groups() const { return (int64_t)spg_ns * 45 / 100; }
     PooledBuf d_sub_cnt;       // STATIC: [owners][K1 CTAs] rows per segment
     static constexpr int SPG_STATIC_CNT_SLOTS = 128;  // table slots given up for the segment counters (512 x 4 B)
     bool spg_hot_enabled = true, spg_hot_sampled = false;  // heavy-hitter table: sampled once per state, at its first SPG launch
@@ -1772,7 +1820,7 @@ class GroupbyState {
         }
     }
 
-    void consume_spg(const long long* keys, const long long* vals, int64_t n, int sum_j, int cnt_j, bool lowcard = false) {
+    void consume_spg(const long long* keys, const long long* vals, int64_t n, int sum_j, int cnt_j, bool lowcard = false, int64_t est_groups = 0) {
         if (!h_spg) {
             h_spg = (long long*)pinned_acquire(24 * sizeof(long long));  // [slot][8] counter snapshots + n_hot read-back
             for (int b = 0; b < 2; b++) B200_CUDA(cudaEventCreateWithFlags(&spg_ev[b], cudaEventDisableTiming));
@@ -1817,7 +1865,13 @@ class GroupbyState {
             a.sum_first = (sum_j >= 0 && cnt_j >= 0 && sum_j < cnt_j) ? 1 : 0; a.ns = spg_ns; a.n_pass = spg_passes;
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (profiling) { B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1)); B200_CUDA(cudaEventRecord(ev0, stream)); }
-            if (lowcard) {
+            if (!lowcard && spg_onepass && est_groups > 0 && est_groups <= spg_onepass_groups()) {
+                a.n_pass = 1;
+                if (sum_j >= 0 && cnt_j >= 0) spg_aggregate_kernel<true, true, false, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+                else if (sum_j >= 0) spg_aggregate_kernel<true, false, false, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+                else spg_aggregate_kernel<false, true, false, true><<<spg_owners, SPG_THREADS, spg_smem, stream>>>(a);
+                launches--;  // one kernel, the accounting below adds two
+            } else if (lowcard) {
                 const bool small = lowcard_small;
                 int gl = (int)std::min<int64_t>((int64_t)sms * (small ? 3 : 2), (rows + LC_THREADS * 2 - 1) / (LC_THREADS * 2));
                 size_t lsm = (size_t)(small ? LC_SLOTS_SMALL : LC_SLOTS_BIG) * 20 + 64;
@@ -1922,13 +1976,13 @@ class GroupbyState {
                 est = n_groups;
                 if (prefix == n) return;
                 for (int c = 0; c < n_cols; c++) if (data[c]) d2[c] = (const char*)data[c] + prefix * ctype_size(c_types[c]);
-                if (spg_pass_count(est) > 0) { spg_passes = spg_pass_count(est); consume_spg((const long long*)d2[0], vcol >= 0 ? (const long long*)d2[vcol] : nullptr, n - prefix, sum_j, cnt_j, lc_pick(est)); }
+                if (spg_pass_count(est) > 0) { spg_passes = spg_pass_count(est); consume_spg((const long long*)d2[0], vcol >= 0 ? (const long long*)d2[vcol] : nullptr, n - prefix, sum_j, cnt_j, lc_pick(est), est); }
                 else consume_direct(d2, v2, n - prefix, fast, sum_j, cnt_j, vcol, false);
                 return;
             }
             if (force || spg_pass_count(est) > 0) {
                 spg_passes = std::max(1, spg_pass_count(est));
-                consume_spg((const long long*)data[0], vcol >= 0 ? (const long long*)data[vcol] : nullptr, n, sum_j, cnt_j, est > 0 && lc_pick(est));
+                consume_spg((const long long*)data[0], vcol >= 0 ? (const long long*)data[vcol] : nullptr, n, sum_j, cnt_j, est > 0 && lc_pick(est), est);
                 return;
             }
         }

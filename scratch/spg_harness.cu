@@ -4,7 +4,8 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -I bodo_b200/csrc \
 //        scratch/spg_harness.cu bodo_b200/csrc/misc.cu -o scratch/spg_harness
-//   scratch/spg_harness [log2_rows=27] [groups=1000000] [reps=5] [static=0] [cnt_stride_pad_bytes=0]
+//   scratch/spg_harness [log2_rows=27] [groups=1000000] [reps=5] [mode=0] [cnt_stride_pad_bytes=0]
+//       mode 0 = shipping K1 + K2, 1 = STATIC variant, 2 = one-pass variant (K2 over the input columns, no K1; use <= 6000 groups)
 //
 // Prints per-kernel CUDA-event times (min / median over reps), the achieved fraction of the 16 B/row stream roofline for the
 // pair, and checks SUM/COUNT totals against the input (result must be exact).
@@ -39,7 +40,8 @@ int main(int argc, char** argv) {
     const int lg = argc > 1 ? atoi(argv[1]) : 27;
     const uint64_t groups = argc > 2 ? strtoull(argv[2], nullptr, 10) : 1000000ull;
     const int reps = argc > 3 ? atoi(argv[3]) : 5;
-    const bool use_static = argc > 4 && atoi(argv[4]) != 0;
+    const int mode = argc > 4 ? atoi(argv[4]) : 0;
+    const bool use_static = mode == 1, onepass = mode == 2;
     const size_t pad = argc > 5 ? strtoull(argv[5], nullptr, 10) : 0;  // shifts the owner row counters inside their allocation
     const int64_t rows = 1ll << lg;
     int dev = 0, sms = 0, max_smem = 0;
@@ -87,6 +89,7 @@ int main(int argc, char** argv) {
     auto k2 = use_static ? (const void*)spg_aggregate_kernel<true, true, true> : (const void*)spg_aggregate_kernel<true, true, false>;
     CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
     CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem));
+    CK(cudaFuncSetAttribute((const void*)spg_aggregate_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem));
 
     std::vector<float> t1, t2;
     cudaEvent_t e0, e1, e2;
@@ -94,10 +97,12 @@ int main(int argc, char** argv) {
     for (int r = 0; r < reps + 1; r++) {  // the first repetition (table inserts, cold) is not reported
         CK(cudaMemsetAsync(bucket_cnt, 0, (size_t)owners * SPG_CNT_STRIDE * 8));
         CK(cudaEventRecord(e0));
-        if (use_static) spg_partition_tma_kernel<true, true, false, true><<<g1, SPG_TTHREADS, k1_smem>>>(a);
+        if (onepass) {}
+        else if (use_static) spg_partition_tma_kernel<true, true, false, true><<<g1, SPG_TTHREADS, k1_smem>>>(a);
         else spg_partition_tma_kernel<true, true, false, false><<<g1, SPG_TTHREADS, k1_smem>>>(a);
         CK(cudaEventRecord(e1));
-        if (use_static) spg_aggregate_kernel<true, true, true><<<owners, SPG_THREADS, k2_smem>>>(a);
+        if (onepass) spg_aggregate_kernel<true, true, false, true><<<owners, SPG_THREADS, k2_smem>>>(a);
+        else if (use_static) spg_aggregate_kernel<true, true, true><<<owners, SPG_THREADS, k2_smem>>>(a);
         else spg_aggregate_kernel<true, true, false><<<owners, SPG_THREADS, k2_smem>>>(a);
         CK(cudaEventRecord(e2));
         CK(cudaEventSynchronize(e2));
@@ -120,9 +125,9 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(hc, counters, 64, cudaMemcpyDeviceToHost));
     const bool ok = h[0] == (unsigned long long)rows * (reps + 1) && h[1] == hin * (unsigned long long)(reps + 1) && hc[1] == 0;
     const float m1 = t1[t1.size() / 2], m2 = t2[t2.size() / 2];
-    printf("{\"rows\": %lld, \"groups\": %llu, \"static\": %d, \"k1_ms\": {\"min\": %.4f, \"median\": %.4f}, \"k2_ms\": {\"min\": %.4f, \"median\": %.4f}, "
+    printf("{\"rows\": %lld, \"groups\": %llu, \"mode\": %d, \"k1_ms\": {\"min\": %.4f, \"median\": %.4f}, \"k2_ms\": {\"min\": %.4f, \"median\": %.4f}, "
            "\"pair_grows_per_s\": %.2f, \"roofline_frac\": %.4f, \"table_groups\": %lld, \"retry_rows\": %lld, \"check\": \"%s\"}\n",
-           (long long)rows, (unsigned long long)groups, (int)use_static, t1[0], m1, t2[0], m2, rows / ((m1 + m2) * 1e-3) / 1e9,
+           (long long)rows, (unsigned long long)groups, mode, t1[0], m1, t2[0], m2, rows / ((m1 + m2) * 1e-3) / 1e9,
            rows * 16.0 / ((m1 + m2) * 1e-3) / 6574.8e9, hc[0], hc[1], ok ? "ok" : "MISMATCH");
     return ok ? 0 : 3;
 }
