@@ -57,6 +57,13 @@ def lib():
         L.oracle_hash_inner_32_i32.restype = C.c_uint32
         L.oracle_hash_inner_32_i32.argtypes = [C.c_int32, C.c_uint32]
         L.oracle_hash_to_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_void_p]
+        L.oracle_hash_combine_boost.restype = C.c_uint32
+        L.oracle_hash_combine_boost.argtypes = [C.c_uint32, C.c_uint32]
+        L.oracle_py_hash_double.restype = C.c_int64
+        L.oracle_py_hash_double.argtypes = [C.c_double]
+        L.oracle_hash_inner_32_f64.restype = C.c_uint32
+        L.oracle_hash_inner_32_f64.argtypes = [C.c_double, C.c_uint32]
+        L.oracle_hash_keys_i64.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_void_p]
         L.oracle_shuffle_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
         L.oracle_hash_join.restype = C.c_int64
         L.oracle_hash_join.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
@@ -152,6 +159,18 @@ def hash_to_rank(keys, key_valid, n_pes, seed=SEED_HASH_PARTITION):
     bm = _bitmap(key_valid)
     out = np.empty(len(k), dtype=np.int32)
     lib().oracle_hash_to_rank(k.ctypes.data, None if bm is None else bm.ctypes.data, len(k), n_pes, seed, out.ctypes.data)
+    return out
+
+
+def hash_keys(key_cols, key_valids=None, seed=SEED_HASH_PARTITION):
+    """hash_keys over 1..n int64 key columns (first hashed, the rest combined); returns uint32 hashes."""
+    cols = [np.ascontiguousarray(k, dtype=np.int64) for k in key_cols]
+    n = len(cols[0])
+    bms = [_bitmap(v) for v in (key_valids or [None] * len(cols))]
+    kp = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    vp = (C.c_void_p * len(cols))(*[None if b is None else b.ctypes.data for b in bms])
+    out = np.empty(n, dtype=np.uint32)
+    lib().oracle_hash_keys_i64(kp, vp, len(cols), n, seed, out.ctypes.data)
     return out
 
 

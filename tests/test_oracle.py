@@ -129,3 +129,68 @@ def test_synth_generators_agree(oracle):
     k2, v2 = synth.numpy_fill(12345, 10_000, 777, 3)
     np.testing.assert_array_equal(k1, k2)
     np.testing.assert_array_equal(v1, v2)
+
+
+# ---- multi-column / float key hashing ---------------------------------------------------------------
+def test_py_hash_double_matches_the_interpreter(oracle):
+    # the reference hashes float keys through CPython's _Py_HashDouble (bodo/libs/_array_hash.cpp:119-170); the oracle's
+    # restatement is pinned against hash(float) of the interpreter running the tests (same algorithm since 3.2; NaN
+    # hashes by identity since 3.10 and the reference passes a NULL identity -> 0)
+    import math
+    import random
+    import struct
+
+    L = oracle.lib()
+    vals = [0.0, -0.0, 1.0, -1.0, 0.5, 1e300, -1e300, 1e-300, 5e-324, float("inf"), float("-inf"), math.pi, 2.0**61, 2.0**61 - 1,
+            2.0**62 + 12345.0, -7.25, 1 / 3, 123456789.0, -2.0**31]
+    rnd = random.Random(7)
+    vals += [rnd.uniform(-1e6, 1e6) for _ in range(500)]
+    vals += [struct.unpack("<d", struct.pack("<Q", rnd.getrandbits(64)))[0] for _ in range(3000)]
+    for v in vals:
+        if math.isnan(v):
+            assert L.oracle_py_hash_double(v) == 0
+        else:
+            assert L.oracle_py_hash_double(v) == hash(v), v
+    assert L.oracle_py_hash_double(float("nan")) == 0
+    # float key hash = hash_inner_32 of that Py_hash_t
+    assert L.oracle_hash_inner_32_f64(2.5, 0xB0D01289) == L.oracle_hash_inner_32_i64(hash(2.5), 0xB0D01289)
+
+
+def test_hash_combine_boost_is_one_murmur3_round(oracle):
+    # hash_combine_boost (bodo/libs/_array_hash.cpp:41-56) is the body round of MurmurHash3_x86_32: seed -> one 4-byte
+    # block -> finalizer must reproduce the published MurmurHash3 verification vectors
+    L = oracle.lib()
+
+    def fmix32(h):
+        h ^= h >> 16
+        h = (h * 0x85EBCA6B) & 0xFFFFFFFF
+        h ^= h >> 13
+        h = (h * 0xC2B2AE35) & 0xFFFFFFFF
+        return h ^ (h >> 16)
+
+    def murmur3_one_block(k1, seed):
+        return fmix32(L.oracle_hash_combine_boost(seed, k1) ^ 4)
+
+    assert murmur3_one_block(0xFFFFFFFF, 0) == 0x76293B50
+    assert murmur3_one_block(0x87654321, 0) == 0xF55B516B
+    assert murmur3_one_block(0x87654321, 0x5082EDEE) == 0x2362F9DE
+
+
+def test_hash_keys_first_column_hashed_rest_combined(oracle):
+    rng = np.random.default_rng(2)
+    k0, k1, k2 = (rng.integers(-2**40, 2**40, 1000) for _ in range(3))
+    v1 = rng.random(1000) > 0.1
+    L = oracle.lib()
+    seed = oracle.SEED_HASH_PARTITION
+    one = oracle.hash_keys([k0])
+    assert [int(x) for x in one[:50]] == [L.oracle_hash_inner_32_i64(int(x), seed) for x in k0[:50]]
+    three = oracle.hash_keys([k0, k1, k2], [None, v1, None])
+    na = L.oracle_hash_inner_32_i64(1, seed)
+    for i in range(0, 1000, 37):
+        h = L.oracle_hash_inner_32_i64(int(k0[i]), seed)
+        h = L.oracle_hash_combine_boost(h, L.oracle_hash_inner_32_i64(int(k1[i]), seed) if v1[i] else na)
+        h = L.oracle_hash_combine_boost(h, L.oracle_hash_inner_32_i64(int(k2[i]), seed))
+        assert int(three[i]) == h
+    # column order matters (the combine is not commutative), equal rows hash equally
+    assert not np.array_equal(oracle.hash_keys([k0, k1]), oracle.hash_keys([k1, k0]))
+    assert np.array_equal(oracle.hash_keys([k0[:10], k1[:10]]), oracle.hash_keys([k0[:10].copy(), k1[:10].copy()]))
