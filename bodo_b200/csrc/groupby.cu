@@ -636,7 +636,11 @@ constexpr int SPG_MAX_OWNERS = 256;
 // K1 reserves one run per owner per tile with a global atomic on the owner's row counter: ~10^7 atomics per launch.  With
 // the 148 counters packed into ten cache lines K1's speed depended on where the array happened to land (0.80 ms against
 // 1.00 ms per 2^27 rows for the same SASS after an unrelated allocation moved it), so every counter gets its own line.
+#ifdef SPG_CNT_STRIDE_OVERRIDE  // scratch/spg_harness experiments only
+constexpr int SPG_CNT_STRIDE = SPG_CNT_STRIDE_OVERRIDE;
+#else
 constexpr int SPG_CNT_STRIDE = 16;
+#endif
 constexpr int SPG_STASH = 1024;     // K2: linear-probing stash slots for keys whose two buckets are full
 
 struct SpgArgs {
