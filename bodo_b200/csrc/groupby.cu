@@ -893,8 +893,8 @@ __global__ void __launch_bounds__(SPG_TTHREADS, SPG_TCTAS) spg_partition_tma_ker
     unsigned int* hhi = hlo + SPG_HOT_SLOTS;
     unsigned int* hcnt = hhi + SPG_HOT_SLOTS;
     const int G = a.n_owners, tid = threadIdx.x;
-    constexpr bool hot_on = HOT;  // separate instantiation: the uniform-key kernel carries none of this (measured: the
-                                  // same code with a run-time flag cost K1 24 % even when the flag was off)
+    constexpr bool hot_on = HOT;  // separate instantiation: the uniform-key kernel carries none of this (its SASS is the
+                                  // kernel tuned before heavy hitters existed)
     if (hot_on)
         for (int s = tid; s < SPG_HOT_SLOTS; s += SPG_TTHREADS) { hkeys[s] = a.hot_tab[s]; hlo[s] = 0; hhi[s] = 0; hcnt[s] = 0; }
     constexpr int ROWS = SPG_TILE / SPG_TTHREADS;
