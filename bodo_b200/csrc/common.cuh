@@ -147,8 +147,13 @@ inline int num_sms(int device) {
 // Scratch buffers (bucket / retry / fail lists: up to GBs) come from a process-wide per-device pool and go back to
 // it when a state dies, so creating an operator state per query does not pay cudaMalloc / cudaFree of gigabytes
 // (cudaFree of multi-GB blocks is synchronous and costs tens of milliseconds).
+// The pool is stream-ordered: a released block remembers an event recorded on the releasing thread's scratch stream
+// (scratch_set_stream: every state entry point sets it to the state's stream) and is only handed out again once that
+// event has completed.  Pooled bytes are capped (B200_POOL_MAX_BYTES, default 24 GiB; scratch_trim frees on request).
 void* scratch_acquire(int device, size_t bytes, size_t* got);
 void scratch_release(int device, void* p, size_t bytes);
+void scratch_set_stream(cudaStream_t s);
+void scratch_trim(int device, size_t keep_bytes);
 void* pinned_acquire(size_t bytes);   // small pinned host blocks (counter mirrors), pooled for the same reason
 void pinned_release(void* p, size_t bytes);
 

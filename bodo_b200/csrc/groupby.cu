@@ -1471,7 +1471,7 @@ class GroupbyState {
             B200_REQUIRE(arr_types[kc] == ARR_NUMPY || arr_types[kc] == ARR_NULLABLE, "b200 groupby: unsupported key array type");
         }
         if (!parallel) { n_pes = 1; rank = 0; }
-        B200_CUDA(cudaSetDevice(device));
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         sms = num_sms(device);
         for (int j = 0; j < n_funcs; j++) {
             FuncSpec f{};
@@ -1531,6 +1531,7 @@ class GroupbyState {
 
     ~GroupbyState() {
         cudaSetDevice(device);
+        scratch_set_stream(stream);
         cudaStreamSynchronize(stream);
         if (getenv("B200_TRACE"))
             fprintf(stderr, "[b200 groupby state] ctor %.3f ms, grow %.3f ms (%lld rebuilds), spg alloc %.3f ms, spg loop %.3f ms, finalize %.3f ms, cap %llu\n",
@@ -1798,6 +1799,9 @@ class GroupbyState {
             read_counters();
             uint64_t nc = cap;
             int64_t pending = h_counters[1] + h_counters[6];
+            // the snapshot this call was made on may be stale: the other slot's spg_finish already grew the table and merged
+            // BOTH retry lists (their live counters are 0 then) — nothing left to do, and no second grow
+            if (pending == 0) break;
             while (nc < 2ull * (uint64_t)(n_groups + pending + (int64_t)spg_owners * spg_ns)) nc <<= 1;
             if (nc == cap) nc <<= 1;
             grow(nc);
@@ -2051,7 +2055,7 @@ class GroupbyState {
     void consume(const b200_table* t) {
         B200_REQUIRE(!build_done, "b200 groupby: consume after the build was finished");
         B200_REQUIRE(t->n_cols == n_cols, "b200 groupby: batch has a different number of columns than the build schema");
-        B200_CUDA(cudaSetDevice(device));
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         int64_t n = t->n_rows;
         std::vector<bool> used(n_cols, false);
         for (int kc = 0; kc < nk; kc++) used[kc] = true;
@@ -2137,7 +2141,7 @@ class GroupbyState {
         if (finalized) return n_out;
         double tf0 = now();
         struct Acc3 { double& t; double t0; ~Acc3() { t += now() - t0; } } acc3{t_finalize, tf0};
-        B200_CUDA(cudaSetDevice(device));
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         compact();
         const int64_t max_out = n_groups_bound + 2;  // group count (+ the two special slots) from compact()'s read-back
         EvalArgs e{};
@@ -2183,7 +2187,7 @@ class GroupbyState {
 
     // ---- exchange ----
     int64_t shuffle_prepare(int64_t* send_counts) {
-        B200_CUDA(cudaSetDevice(device));
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         build_done = true;
         compact();
         read_counters();
@@ -2212,7 +2216,7 @@ class GroupbyState {
         return p;
     }
     void shuffle_pack(void* send_buf) {
-        B200_CUDA(cudaSetDevice(device));
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         // exclusive scan of the per-destination counts -> running cursors
         std::vector<long long> offs(n_pes, 0);
         long long run = 0;
@@ -2229,7 +2233,7 @@ class GroupbyState {
         n_groups = 0; n_groups_bound = 0; untracked_groups = 0;
     }
     void shuffle_combine(const void* recv, int64_t n_rows) {
-        B200_CUDA(cudaSetDevice(device));
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         if (n_rows == 0) return;
         B200_REQUIRE(n_rows < (1ll << 32), "b200 groupby: too many partial rows in one combine call");
         bool could_fail = (int64_t)(cap / 2) - n_groups_bound < n_rows;

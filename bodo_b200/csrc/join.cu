@@ -13,7 +13,10 @@
 //            unlike the cuDF path bodo/libs/streaming/cuda_join.cpp:543-612).
 //   outer  : probe_table_outer emits unmatched probe rows with NULL build columns; build_table_outer tracks
 //            matched build rows and emits the unmatched ones after the last probe batch.
-// NA keys match NA keys (pandas semantics, is_na_equal = true, bodo/pandas/physical/join.h:267).
+// NA keys: `is_na_equal` is a state option, as in the reference's HashJoinState.  true (the pandas door,
+// bodo/pandas/physical/join.h:267): NA joins NA.  false (the default of join_state_init_py_entry, SQL semantics): rows
+// with an NA key never match — they are filtered from the build table unless it is the outer side
+// (_join.cpp:3180 filter_na_values) and only survive as NULL-extended rows of an outer join.
 #include <algorithm>
 #include <vector>
 
@@ -133,12 +136,14 @@ __device__ __forceinline__ uint32_t j_find(const long long* __restrict__ tkeys, 
 
 // BuildHashTable: slot per distinct key, num_rows_in_group, build_row_to_group_map (= row_slot)
 __global__ void join_insert_count_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid_bytes, int64_t n,
-                                         long long* tkeys, uint64_t cap, SlotInfo* info, uint32_t* row_slot) {
+                                         long long* tkeys, uint64_t cap, SlotInfo* info, uint32_t* row_slot, int na_equal) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t s;
-        if (key_valid_bytes && !key_valid_bytes[i]) s = (uint32_t)cap;  // NA group
-        else {
+        if (key_valid_bytes && !key_valid_bytes[i]) {
+            if (!na_equal) { row_slot[i] = J_NONE; continue; }  // never matches: belongs to no group
+            s = (uint32_t)cap;  // NA group
+        } else {
             long long key = load_int_as_i64(key_data, key_ctype, i);
             s = key == J_EMPTY ? (uint32_t)cap + 1 : j_find_or_insert(tkeys, cap, key);
         }
@@ -161,18 +166,18 @@ __global__ void join_fill_groups_kernel(const uint32_t* row_slot, int64_t n, con
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t s = row_slot[i];
-        if (info[s].cnt > 1) groups[offs[s] + atomicAdd(&fill[s], 1u)] = (uint32_t)i;
+        if (s != J_NONE && info[s].cnt > 1) groups[offs[s] + atomicAdd(&fill[s], 1u)] = (uint32_t)i;
     }
 }
 
 // probe pass A: slot + match count per probe row
 __global__ void join_probe_count_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid, int64_t n,
                                         const long long* tkeys, uint64_t cap, const SlotInfo* info, int probe_outer,
-                                        uint32_t* pslot, uint32_t* pcnt) {
+                                        uint32_t* pslot, uint32_t* pcnt, int na_equal) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t s;
-        if (!bit_valid(key_valid, i)) s = (uint32_t)cap;
+        if (!bit_valid(key_valid, i)) s = na_equal ? (uint32_t)cap : J_NONE;
         else {
             long long key = load_int_as_i64(key_data, key_ctype, i);
             s = key == J_EMPTY ? (uint32_t)cap + 1 : j_find(tkeys, cap, key);
@@ -329,6 +334,7 @@ struct FastProbeArgs {
     const unsigned long long* bpack; int n_fields;
     unsigned long long* cursor;
     int n_b, n_p;
+    int na_equal;
     int b_field[J_MAX_COLS];               // kept build col -> payload field index, -1 = the key column
     const uint8_t* b_valid[J_MAX_COLS]; int b_size[J_MAX_COLS];
     const void* p_data[J_MAX_COLS]; const uint8_t* p_valid[J_MAX_COLS]; int p_size[J_MAX_COLS];
@@ -365,7 +371,7 @@ __global__ void __launch_bounds__(256) join_probe_fast_kernel(const __grid_const
             if (i < a.n_probe) {
                 kvalid[r] = bit_valid(a.key_valid, i);
                 key[r] = load_int_as_i64(a.key_data, a.key_ctype, i);
-                if (!kvalid[r]) { Slot16 e = a.slots[a.cap]; match[r] = e.cnt > 0; brow[r] = e.first; }
+                if (!kvalid[r]) { if (a.na_equal) { Slot16 e = a.slots[a.cap]; match[r] = e.cnt > 0; brow[r] = e.first; } }
                 else if (key[r] == J_EMPTY) { Slot16 e = a.slots[a.cap + 1]; match[r] = e.cnt > 0; brow[r] = e.first; }
                 else {
                     uint64_t s = j_hash_slot(key[r], mask);
@@ -440,6 +446,7 @@ class JoinState {
     std::vector<int8_t> b_ct, b_at, p_ct, p_at;
     int n_b, n_p;
     bool build_outer, probe_outer;
+    bool na_equal = false;  // is_na_equal of the reference's HashJoinState
     int64_t output_batch_size;
     // build side
     std::vector<GrowCol> bcol, bvalid;  // data; validity as one byte per row (empty when the column has none so far)
@@ -461,24 +468,33 @@ class JoinState {
     bool tail_emitted = false;
 
     JoinState(const int8_t* bct, const int8_t* bat, int nb, const int8_t* pct, const int8_t* pat, int np, uint64_t n_keys,
-              bool bo, bool po, int64_t obs, int dev, int64_t expected_build_rows, cudaStream_t st)
-        : device(dev), stream(st), n_b(nb), n_p(np), build_outer(bo), probe_outer(po), output_batch_size(obs) {
+              bool bo, bool po, bool na_eq, int64_t obs, int dev, int64_t expected_build_rows, cudaStream_t st)
+        : device(dev), stream(st), n_b(nb), n_p(0), build_outer(bo), probe_outer(po), na_equal(na_eq), output_batch_size(obs) {
         B200_REQUIRE(n_keys == 1, "b200 join: exactly one key column is supported (multi-key is a 'next' row, SURVEY.md §8f)");
-        B200_REQUIRE(nb >= 1 && np >= 1 && nb <= J_MAX_COLS && np <= J_MAX_COLS, "b200 join: between 1 and 32 columns per side");
-        b_ct.assign(bct, bct + nb); b_at.assign(bat, bat + nb); p_ct.assign(pct, pct + np); p_at.assign(pat, pat + np);
+        B200_REQUIRE(nb >= 1 && np >= 0 && nb <= J_MAX_COLS && np <= J_MAX_COLS, "b200 join: between 1 and 32 columns per side");
+        b_ct.assign(bct, bct + nb); b_at.assign(bat, bat + nb);
         for (int c = 0; c < nb; c++) B200_REQUIRE(ctype_size(b_ct[c]) > 0, "b200 join: unsupported build column dtype");
-        for (int c = 0; c < np; c++) B200_REQUIRE(ctype_size(p_ct[c]) > 0, "b200 join: unsupported probe column dtype");
-        B200_REQUIRE(!ctype_is_float(b_ct[0]) && !ctype_is_float(p_ct[0]), "b200 join: key columns must be integer/date typed");
-        B200_REQUIRE(ctype_size(b_ct[0]) == ctype_size(p_ct[0]), "b200 join: build and probe key widths differ");
-        B200_CUDA(cudaSetDevice(device));
+        B200_REQUIRE(!ctype_is_float(b_ct[0]), "b200 join: key columns must be integer/date typed");
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         sms = num_sms(device);
         bcol.resize(nb); bvalid.resize(nb); b_has_valid.assign(nb, false);
         if (expected_build_rows > 0)
             for (int c = 0; c < nb; c++) bcol[c].reserve((size_t)expected_build_rows * ctype_size(b_ct[c]));
-        out_data.resize(nb + np); out_vbytes.resize(nb + np); out_bitmap.resize(nb + np);
-        stage_data.resize(std::max(nb, np)); stage_valid.resize(std::max(nb, np));
+        stage_data.resize(nb); stage_valid.resize(nb);
+        if (np > 0) set_probe_schema(pct, pat, np);
     }
-    ~JoinState() { cudaSetDevice(device); cudaStreamSynchronize(stream); pinned_release(h_cursor, 8); }
+    // The probe schema may be given at init (n_probe_arrs > 0) or adopted from the first probe batch (n_probe_arrs == 0), so
+    // a host layer that only learns it from the data can feed build batches straight away.
+    void set_probe_schema(const int8_t* pct, const int8_t* pat, int np) {
+        B200_REQUIRE(np >= 1 && np <= J_MAX_COLS, "b200 join: between 1 and 32 columns per side");
+        p_ct.assign(pct, pct + np); p_at.assign(pat, pat + np); n_p = np;
+        for (int c = 0; c < np; c++) B200_REQUIRE(ctype_size(p_ct[c]) > 0, "b200 join: unsupported probe column dtype");
+        B200_REQUIRE(!ctype_is_float(p_ct[0]), "b200 join: key columns must be integer/date typed");
+        B200_REQUIRE(ctype_size(b_ct[0]) == ctype_size(p_ct[0]), "b200 join: build and probe key widths differ");
+        out_data.resize(n_b + np); out_vbytes.resize(n_b + np); out_bitmap.resize(n_b + np);
+        if ((int)stage_data.size() < std::max(n_b, np)) { stage_data.resize(std::max(n_b, np)); stage_valid.resize(std::max(n_b, np)); }
+    }
+    ~JoinState() { cudaSetDevice(device); scratch_set_stream(stream); cudaStreamSynchronize(stream); pinned_release(h_cursor, 8); }
 
     int grid_for(int64_t n) const { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sms * 8)); }
 
@@ -509,9 +525,10 @@ class JoinState {
     void build_consume(const b200_table* t, bool is_last) {
         B200_REQUIRE(!build_final, "b200 join: build batch after the build was finalized");
         B200_REQUIRE(t->n_cols == n_b, "b200 join: build batch has a different number of columns than the schema");
-        B200_CUDA(cudaSetDevice(device));
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         int64_t n = t->n_rows;
-        B200_REQUIRE(n_build + n < (1ll << 32) - 2, "b200 join: build side is limited to 2^32 - 2 rows per GPU");
+        // slot ids and build row ids are 32-bit; cap = next power of two >= 2 * n_build, and cap + 2 must stay below 2^32
+        B200_REQUIRE(n_build + n <= (1ll << 30), "b200 join: build side is limited to 2^30 rows per GPU");
         if (n > 0) {
             std::vector<const void*> data; std::vector<const uint8_t*> valid;
             stage_batch(t, n_b, b_ct, data, valid);
@@ -547,7 +564,7 @@ class JoinState {
         launches++;
         if (n_build > 0) {
             join_insert_count_kernel<<<grid_for(n_build), 256, 0, stream>>>(bcol[0].buf.p, b_ct[0], b_has_valid[0] ? bvalid[0].buf.as<uint8_t>() : nullptr,
-                                                                           n_build, d_tkeys.as<long long>(), cap, d_info.as<SlotInfo>(), d_row_slot.as<uint32_t>());
+                                                                           n_build, d_tkeys.as<long long>(), cap, d_info.as<SlotInfo>(), d_row_slot.as<uint32_t>(), na_equal ? 1 : 0);
             d_cnt_multi.alloc(n_slots * 4);
             join_slot_counts_kernel<<<grid_for((int64_t)n_slots), 256, 0, stream>>>(d_info.as<SlotInfo>(), n_slots, d_cnt_multi.as<uint32_t>());
             launches += 2;
@@ -623,7 +640,7 @@ class JoinState {
             FastProbeArgs f{};
             f.n_probe = n; f.key_data = data[0]; f.key_ctype = p_ct[0]; f.key_valid = valid[0];
             f.slots = d_slots16.as<Slot16>(); f.cap = cap; f.bpack = d_bpack.as<unsigned long long>(); f.n_fields = std::max(n_b - 1, 1);
-            f.cursor = d_cursor.as<unsigned long long>(); f.n_b = (int)kb.size(); f.n_p = (int)kp.size();
+            f.cursor = d_cursor.as<unsigned long long>(); f.n_b = (int)kb.size(); f.n_p = (int)kp.size(); f.na_equal = na_equal ? 1 : 0;
             for (int k = 0; k < n_out_cols; k++) {
                 bool is_b = k < (int)kb.size();
                 int src = is_b ? kb[k] : kp[k - kb.size()];
@@ -657,9 +674,15 @@ class JoinState {
     int64_t probe_consume(const b200_table* t, const uint64_t* kept_b, int64_t n_kb, const uint64_t* kept_p, int64_t n_kp,
                           b200_table* out, bool is_last) {
         B200_REQUIRE(build_final, "b200 join: probe before the build side was finished (is_last build batch)");
+        if (n_p == 0) {  // adopt the probe schema from the first probe batch
+            B200_REQUIRE(t->n_cols >= 1 && t->n_cols <= J_MAX_COLS, "b200 join: between 1 and 32 columns per side");
+            std::vector<int8_t> ct(t->n_cols), at(t->n_cols);
+            for (int c = 0; c < t->n_cols; c++) { ct[c] = (int8_t)t->cols[c].c_type; at[c] = (int8_t)t->cols[c].arr_type; }
+            set_probe_schema(ct.data(), at.data(), t->n_cols);
+        }
         B200_REQUIRE(t->n_cols == n_p, "b200 join: probe batch has a different number of columns than the schema");
         B200_REQUIRE(out->cols != nullptr, "b200 join: out->cols must point to n_kept_build + n_kept_probe descriptors");
-        B200_CUDA(cudaSetDevice(device));
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         std::vector<int> kb, kp;
         for (int64_t k = 0; k < n_kb; k++) { B200_REQUIRE((int)kept_b[k] < n_b, "b200 join: bad kept build column"); kb.push_back((int)kept_b[k]); }
         for (int64_t k = 0; k < n_kp; k++) { B200_REQUIRE((int)kept_p[k] < n_p, "b200 join: bad kept probe column"); kp.push_back((int)kept_p[k]); }
@@ -674,7 +697,7 @@ class JoinState {
         d_pslot.ensure((size_t)(n + 1) * 4); d_pcnt.ensure((size_t)(n + 1) * 4); d_poff.ensure((size_t)(n + 2) * 8);
         if (n > 0) {
             join_probe_count_kernel<<<grid_for(n), 256, 0, stream>>>(data[0], p_ct[0], valid[0], n, d_tkeys.as<long long>(), cap, d_info.as<SlotInfo>(),
-                                                                     probe_outer ? 1 : 0, d_pslot.as<uint32_t>(), d_pcnt.as<uint32_t>());
+                                                                     probe_outer ? 1 : 0, d_pslot.as<uint32_t>(), d_pcnt.as<uint32_t>(), na_equal ? 1 : 0);
             launches++;
             B200_CUDA(cudaMemsetAsync(d_pcnt.as<uint32_t>() + n, 0, 4, stream));
             n_match = scan.run(d_pcnt.as<uint32_t>(), n + 1, d_poff.as<unsigned long long>(), stream, &launches);
@@ -793,14 +816,14 @@ extern "C" {
 void* b200_join_state_init(int64_t operator_id, const int8_t* build_arr_c_types, const int8_t* build_arr_array_types,
                            int32_t n_build_arrs, const int8_t* probe_arr_c_types, const int8_t* probe_arr_array_types,
                            int32_t n_probe_arrs, uint64_t n_keys, int32_t build_table_outer, int32_t probe_table_outer,
-                           int64_t output_batch_size, int32_t device, int64_t expected_build_rows, void* stream) {
+                           int32_t is_na_equal, int64_t output_batch_size, int32_t device, int64_t expected_build_rows, void* stream) {
     (void)operator_id;
     try {
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw b200::Error("b200 join: no CUDA device available (this path has no CPU fallback)");
         B200_REQUIRE(device >= 0 && device < ndev, "b200 join: bad device ordinal");
         return new JoinState(build_arr_c_types, build_arr_array_types, n_build_arrs, probe_arr_c_types, probe_arr_array_types, n_probe_arrs,
-                             n_keys, build_table_outer != 0, probe_table_outer != 0, output_batch_size, device, expected_build_rows, (cudaStream_t)stream);
+                             n_keys, build_table_outer != 0, probe_table_outer != 0, is_na_equal != 0, output_batch_size, device, expected_build_rows, (cudaStream_t)stream);
     } catch (const std::exception& e) { b200::set_last_error(e.what()); return nullptr; }
 }
 

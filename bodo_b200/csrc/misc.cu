@@ -1,4 +1,5 @@
 // misc.cu — error reporting, runtime probes, raw memory helpers and the synthetic-table generator.
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -6,15 +7,47 @@
 
 namespace b200 {
 namespace {
-struct PoolEntry { void* p; size_t bytes; };
+// A pooled block carries the event recorded on the releasing thread's scratch stream (scratch_set_stream) when it was
+// released: DevBuf::ensure() may hand a block back while kernels that read it are still queued, so whoever acquires the
+// block next (possibly another state on another stream) first waits for that event.  The pool is stream-ordered.
+struct PoolEntry { void* p; size_t bytes; cudaEvent_t ev; };
 std::mutex g_pool_mutex;
 std::vector<PoolEntry> g_pool[64];
+size_t g_pool_bytes[64] = {0};
+thread_local cudaStream_t g_scratch_stream = nullptr;
+
+size_t pool_cap_bytes() {
+    static size_t cap = [] {
+        const char* e = getenv("B200_POOL_MAX_BYTES");
+        return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)24 << 30);
+    }();
+    return cap;
+}
+void wait_and_drop_event(cudaEvent_t ev) {
+    if (!ev) return;
+    cudaEventSynchronize(ev);
+    cudaEventDestroy(ev);
+}
+// caller holds g_pool_mutex
+void trim_locked(int device, size_t keep_bytes) {
+    auto& v = g_pool[device & 63];
+    while (g_pool_bytes[device & 63] > keep_bytes && !v.empty()) {
+        int big = 0;
+        for (int i = 1; i < (int)v.size(); i++) if (v[i].bytes > v[big].bytes) big = i;
+        wait_and_drop_event(v[big].ev);
+        cudaFree(v[big].p);
+        g_pool_bytes[device & 63] -= v[big].bytes;
+        v.erase(v.begin() + big);
+    }
+}
 }  // namespace
+
+void scratch_set_stream(cudaStream_t s) { g_scratch_stream = s; }
 
 void* scratch_acquire(int device, size_t bytes, size_t* got) {
     if (bytes == 0) bytes = 8;
     {
-        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        std::unique_lock<std::mutex> lk(g_pool_mutex);
         auto& v = g_pool[device & 63];
         // best fit, but never hand out a block more than 2x (+1 MiB) larger than asked for
         size_t limit = bytes * 2 + (1u << 20);
@@ -24,6 +57,9 @@ void* scratch_acquire(int device, size_t bytes, size_t* got) {
         if (best >= 0) {
             PoolEntry e = v[best];
             v.erase(v.begin() + best);
+            g_pool_bytes[device & 63] -= e.bytes;
+            lk.unlock();
+            wait_and_drop_event(e.ev);  // work queued on the block before its release has finished
             *got = e.bytes;
             return e.p;
         }
@@ -36,8 +72,7 @@ void* scratch_acquire(int device, size_t bytes, size_t* got) {
         cudaGetLastError();
         {
             std::lock_guard<std::mutex> lk(g_pool_mutex);
-            for (auto& e : g_pool[device & 63]) cudaFree(e.p);
-            g_pool[device & 63].clear();
+            trim_locked(device, 0);
         }
         B200_CUDA(cudaMalloc(&p, bytes));
     }
@@ -46,8 +81,24 @@ void* scratch_acquire(int device, size_t bytes, size_t* got) {
 }
 void scratch_release(int device, void* p, size_t bytes) {
     if (!p) return;
+    cudaEvent_t ev = nullptr;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != device) cudaSetDevice(device);
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+        if (cudaEventRecord(ev, g_scratch_stream) != cudaSuccess) { cudaGetLastError(); cudaEventDestroy(ev); ev = nullptr; cudaDeviceSynchronize(); }
+    } else { cudaGetLastError(); ev = nullptr; cudaDeviceSynchronize(); }
+    if (cur != device && cur >= 0) cudaSetDevice(cur);
     std::lock_guard<std::mutex> lk(g_pool_mutex);
-    g_pool[device & 63].push_back({p, bytes});
+    g_pool[device & 63].push_back({p, bytes, ev});
+    g_pool_bytes[device & 63] += bytes;
+    // bounded: blocks beyond the cap go back to the driver (largest first), so a process that also runs torch's caching
+    // allocator on the same GPU gets the memory back after the states that needed it are gone
+    if (g_pool_bytes[device & 63] > pool_cap_bytes()) trim_locked(device, pool_cap_bytes());
+}
+void scratch_trim(int device, size_t keep_bytes) {
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    trim_locked(device, keep_bytes);
 }
 
 namespace { std::vector<PoolEntry> g_pinned; }
@@ -105,6 +156,10 @@ void* b200_device_malloc(int32_t device, int64_t nbytes) {
         B200_CUDA(cudaMalloc(&p, (size_t)(nbytes > 0 ? nbytes : 8)));
         return p;
     } catch (const std::exception& e) { b200::set_last_error(e.what()); return nullptr; }
+}
+int64_t b200_pool_trim(int32_t device, int64_t keep_bytes) {
+    b200::scratch_trim(device, keep_bytes > 0 ? (size_t)keep_bytes : 0);
+    return 0;
 }
 void b200_device_free(int32_t device, void* p) {
     if (!p) return;

@@ -284,7 +284,7 @@ int b200_shuffle_partition(const b200_table* in_table, int64_t n_keys, int32_t n
 int b200_merge_segment_bitmaps(const uint8_t* segments, const int64_t* counts, int32_t n_src, uint8_t* out_bitmap, int32_t device, void* stream) {
     try {
         B200_REQUIRE(segments && counts && out_bitmap && n_src >= 1 && n_src <= b200::MAX_PES, "b200_merge_segment_bitmaps: bad arguments");
-        B200_CUDA(cudaSetDevice(device));
+        B200_CUDA(cudaSetDevice(device)); b200::scratch_set_stream((cudaStream_t)stream);
         std::vector<long long> row_off(n_src + 1, 0), byte_off(n_src, 0);
         long long bytes = 0;
         for (int j = 0; j < n_src; j++) { row_off[j + 1] = row_off[j] + counts[j]; byte_off[j] = bytes; bytes += (counts[j] + 7) >> 3; }

@@ -128,6 +128,7 @@ class PhysicalJoin:
     def __init__(self, build_key: int, probe_key: int, build_names, probe_names, how: str = "inner", **kw):
         build_outer = how in ("right", "outer")   # the build side is the RIGHT table (reference convention)
         probe_outer = how in ("left", "outer")
+        kw.setdefault("is_na_equal", True)  # pandas merge semantics: NA joins NA (bodo/pandas/physical/join.h:267)
         self.state = J.init_join_state(-1, (build_key,), (probe_key,), tuple(build_names), tuple(probe_names), build_outer, probe_outer, **kw)
 
     def ConsumeBatch(self, batch: Table, prev: OperatorResult) -> OperatorResult:

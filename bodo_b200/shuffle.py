@@ -8,8 +8,9 @@ destination, then ONE all-to-all-v per buffer moves them (torch.distributed -> n
 the reference issues one MPI alltoallv per column buffer, _shuffle.cpp:661-875).  Counts are exchanged first
 (mpi_comm_info's MPI_Alltoall, _shuffle.cpp:210-213).
 
-The exchange logic (`exchange_partitioned`) is backend-agnostic torch.distributed code so it can be exercised on CPU
-with gloo in tests; the partition step itself exists only as a CUDA kernel (no CPU fallback in this package).
+The exchange logic (`exchange_partitioned` / `exchange_table`) is backend-agnostic torch.distributed code (the gloo tests
+drive it on CPU with their own partition and bitmap-merge stand-ins); the partition step and the bitmap merge of
+`shuffle_table` itself exist only as CUDA kernels (no CPU fallback in this package).
 """
 
 from __future__ import annotations
@@ -98,43 +99,60 @@ def exchange_partitioned(buffers: Sequence, send_counts: Sequence[int], validity
 
 
 def merge_segment_bitmaps(bitmap, counts: Sequence[int]):
-    """Concatenate per-source byte-padded bitmaps (one per sending rank) into one contiguous Arrow bitmap.
-    CUDA tensors go through b200_merge_segment_bitmaps (csrc/shuffle.cu); the numpy branch only serves the CPU (gloo)
-    tests of the exchange logic."""
+    """Concatenate per-source byte-padded bitmaps (one per sending rank) into one contiguous Arrow bitmap on the device
+    (b200_merge_segment_bitmaps, csrc/shuffle.cu)."""
     import torch
 
-    if bitmap.is_cuda:
-        n = int(sum(counts))
-        out = torch.zeros(((n + 31) // 32 + 2) * 4, dtype=torch.uint8, device=bitmap.device)
-        cnt = ffi.new("int64_t[]", [int(c) for c in counts])
-        _lib.check(_lib.lib().b200_merge_segment_bitmaps(ffi.cast("uint8_t*", bitmap.data_ptr()), cnt, len(counts),
-                                                         ffi.cast("uint8_t*", out.data_ptr()), bitmap.device.index,
-                                                         ffi.cast("void*", torch.cuda.current_stream(bitmap.device).cuda_stream)),
-                   "merge segment bitmaps")
-        return out
-
-    bits = []
-    off = 0
-    b = bitmap.cpu().numpy()
-    for c in counts:
-        nb = (c + 7) // 8
-        bits.append(np.unpackbits(b[off : off + nb], bitorder="little")[:c])
-        off += nb
-    allbits = np.concatenate(bits) if bits else np.zeros(0, dtype=np.uint8)
-    packed = np.packbits(allbits, bitorder="little")
-    pad = np.zeros((len(packed) + 7) // 8 * 8 + 8, dtype=np.uint8)
-    pad[: len(packed)] = packed
-    return torch.from_numpy(pad).to(bitmap.device)
+    if not bitmap.is_cuda:
+        raise _lib.B200Error("merge_segment_bitmaps: device tensors only (this package has no CPU path)")
+    n = int(sum(counts))
+    out = torch.zeros(((n + 31) // 32 + 2) * 4, dtype=torch.uint8, device=bitmap.device)
+    cnt = ffi.new("int64_t[]", [int(c) for c in counts])
+    _lib.check(_lib.lib().b200_merge_segment_bitmaps(ffi.cast("uint8_t*", bitmap.data_ptr()), cnt, len(counts),
+                                                     ffi.cast("uint8_t*", out.data_ptr()), bitmap.device.index,
+                                                     ffi.cast("void*", torch.cuda.current_stream(bitmap.device).cuda_stream)),
+               "merge segment bitmaps")
+    return out
 
 
-def shuffle_table(table: Table, n_keys: int = 1, parallel: bool = True, keep_comm_info: int = 0, *, group=None, stream: int = 0,
-                  partition_fn: Callable | None = None) -> Table:
+def with_schema_validity(table: Table) -> Table:
+    """Give every NULLABLE column a validity bitmap (all ones when the local data has no nulls).  Whether a bitmap
+    travels must follow from the SCHEMA, not from the local data: Arrow drops the bitmap of a chunk without nulls, and
+    ranks that disagreed on the number of collectives would hang or pair the wrong buffers."""
+    import torch
+
+    cols = []
+    for c in table.columns:
+        if c.arr_type == ArrTypes.NULLABLE_INT_BOOL and c.validity is None:
+            nbytes = (c.length + 7) // 8 + 8
+            if hasattr(c.data, "is_cuda"):
+                v = torch.full((nbytes,), 255, dtype=torch.uint8, device=c.data.device)
+            else:
+                v = np.full(nbytes, 255, dtype=np.uint8)
+            c = Column(c.data, v, c.c_type, c.arr_type, c.length)
+        cols.append(c)
+    return Table(cols, list(table.names))
+
+
+def exchange_table(part: Table, send_counts: Sequence[int], group=None, merge_bitmaps: Callable = merge_segment_bitmaps) -> Table:
+    """All-to-all-v of a destination-grouped table (output of the partition step) and reassembly of the received
+    columns; `merge_bitmaps(recv_bitmap_segments, recv_counts)` turns the per-source bitmap segments into one bitmap."""
+    bufs = [c.data for c in part.columns]
+    vbufs = [c.validity for c in part.columns]
+    rbufs, rvalid, recv_counts = exchange_partitioned(bufs, send_counts, vbufs, group=group)
+    cols = []
+    n_recv = sum(recv_counts)
+    for c, rb, rv in zip(part.columns, rbufs, rvalid):
+        v = merge_bitmaps(rv, recv_counts) if rv is not None else None
+        cols.append(Column(rb, v, c.c_type, c.arr_type if v is None else ArrTypes.NULLABLE_INT_BOOL, n_recv))
+    return Table(cols, list(part.names))
+
+
+def shuffle_table(table: Table, n_keys: int = 1, parallel: bool = True, keep_comm_info: int = 0, *, group=None, stream: int = 0) -> Table:
     """Mirror of bodo.libs.array.shuffle_table(table, n_keys, _is_parallel, keep_comm_info).
 
     Keys are the first n_keys columns (the reference's convention).  Returns this rank's rows after the shuffle
     (order: by source rank, input order within a source — the same as MPI alltoallv of the stable send arrays).
-    `partition_fn(table, n_keys, n_pes) -> (Table, send_counts)` may replace the CUDA partition step; it exists for
-    the CPU (gloo) tests of the exchange logic only.
     """
     import torch
     import torch.distributed as dist
@@ -142,17 +160,6 @@ def shuffle_table(table: Table, n_keys: int = 1, parallel: bool = True, keep_com
     if not parallel or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return table
     n_pes = dist.get_world_size(group)
-    if partition_fn is None:
-        part, send_counts = partition_device(table, n_keys, n_pes, stream)
-        torch.cuda.current_stream().synchronize()
-    else:
-        part, send_counts = partition_fn(table, n_keys, n_pes)
-    bufs = [c.data for c in part.columns]
-    vbufs = [c.validity for c in part.columns]
-    rbufs, rvalid, recv_counts = exchange_partitioned(bufs, send_counts, vbufs, group=group)
-    cols = []
-    n_recv = sum(recv_counts)
-    for c, rb, rv in zip(part.columns, rbufs, rvalid):
-        v = merge_segment_bitmaps(rv, recv_counts) if rv is not None else None
-        cols.append(Column(rb, v, c.c_type, c.arr_type if v is None else ArrTypes.NULLABLE_INT_BOOL, n_recv))
-    return Table(cols, list(part.names))
+    part, send_counts = partition_device(with_schema_validity(table), n_keys, n_pes, stream)
+    torch.cuda.current_stream().synchronize()
+    return exchange_table(part, send_counts, group)

@@ -17,7 +17,7 @@ from ..table import CTable, Table, table_from_ctable
 
 class JoinState:
     def __init__(self, operator_id, build_key_inds, probe_key_inds, build_colnames, probe_colnames, build_outer, probe_outer,
-                 output_batch_size, expected_build_rows, device, stream):
+                 output_batch_size, expected_build_rows, device, stream, is_na_equal=False, build_parallel=False, probe_parallel=False):
         self.operator_id = int(operator_id)
         self.build_key_inds = tuple(int(k) for k in build_key_inds)
         self.probe_key_inds = tuple(int(k) for k in probe_key_inds)
@@ -27,6 +27,9 @@ class JoinState:
         self.probe_colnames = list(probe_colnames) if probe_colnames is not None else None
         self.build_outer = bool(build_outer)
         self.probe_outer = bool(probe_outer)
+        self.is_na_equal = bool(is_na_equal)
+        self.build_parallel = bool(build_parallel)
+        self.probe_parallel = bool(probe_parallel)
         self.output_batch_size = int(output_batch_size)
         self.expected_build_rows = int(expected_build_rows)
         self.device = device
@@ -36,41 +39,52 @@ class JoinState:
         self.build_indices = None
         self.probe_indices = None
         self.build_names = None
-        self._pending_build = []
         self._out = None
 
     def _physical(self, table: Table, key_inds):
         others = [i for i in range(table.n_cols) if i not in key_inds]
         return list(key_inds) + others
 
-    def _init_c(self, probe: Table):
+    def _init_c(self, build: Table):
+        """Create the C state at the first build batch (the probe schema is adopted from the first probe batch, so build
+        batches go straight to the device and the build overlaps whatever produces them)."""
         L = _lib.lib()
         _lib.require_gpu()
         bct, bat = self.build_schema
-        self.probe_indices = self._physical(probe, self.probe_key_inds)
-        pcols = [probe.columns[i] for i in self.probe_indices]
         if self.device is None:
             import torch
 
-            self.device = probe.device if probe.device >= 0 else torch.cuda.current_device()
+            self.device = build.device if build.device >= 0 else torch.cuda.current_device()
         h = L.b200_join_state_init(self.operator_id, ffi.new("int8_t[]", bct), ffi.new("int8_t[]", bat), len(bct),
-                                   ffi.new("int8_t[]", [c.c_type for c in pcols]), ffi.new("int8_t[]", [c.arr_type for c in pcols]),
-                                   len(pcols), 1, int(self.build_outer), int(self.probe_outer), self.output_batch_size, self.device,
-                                   self.expected_build_rows, ffi.cast("void*", self.stream))
+                                   ffi.NULL, ffi.NULL, 0, 1, int(self.build_outer), int(self.probe_outer), int(self.is_na_equal),
+                                   self.output_batch_size, self.device, self.expected_build_rows, ffi.cast("void*", self.stream))
         self.handle = _lib.check_ptr(h, "init_join_state")
 
 
 def init_join_state(operator_id, build_key_inds, probe_key_inds, build_colnames, probe_colnames, build_outer, probe_outer,
                     interval_build_columns=None, force_broadcast=False, op_pool_size_bytes=-1, non_equi_condition=None,
                     build_parallel=False, probe_parallel=False, *, output_batch_size=32768, expected_build_rows=0, device=None,
-                    stream=0) -> JoinState:
-    """Mirror of bodo.libs.streaming.join.init_join_state (join.py:991-1100).  Interval joins, broadcast forcing and
-    non-equi conditions are out of scope and must be left at their defaults."""
+                    stream=0, is_na_equal=False) -> JoinState:
+    """Mirror of bodo.libs.streaming.join.init_join_state (join.py:991-1100).  Interval joins and non-equi conditions are
+    out of scope and must be left at their defaults.
+
+    `is_na_equal` is HashJoinState's option: False is what this door constructs in the reference (join_state_init_py_entry,
+    _join.cpp:4087-4136: NA keys never match); the pandas door (bodo/pandas/physical/join.h:267, here PhysicalJoin / merge)
+    passes True.  `build_parallel` / `probe_parallel` say that the side is row-distributed over the ranks of the default
+    torch.distributed process group: non-owned rows are shuffled to hash_to_rank(key) before they reach the local join
+    (_join.cpp:3243-3300), or — `force_broadcast`, or a build side below the broadcast threshold — the build side is
+    all-gathered instead (:3317-3405)  (see bodo_b200/streaming/dist_join.py)."""
     if interval_build_columns not in (None, (), []) or non_equi_condition is not None:
         raise _lib.B200Error("Streaming Join: interval / non-equi joins are not supported by bodo_b200")
     g = lambda x: getattr(x, "meta", x)
+    if build_parallel or probe_parallel:
+        from .dist_join import DistJoinState
+
+        return DistJoinState(operator_id, g(build_key_inds), g(probe_key_inds), g(build_colnames), g(probe_colnames), build_outer,
+                             probe_outer, output_batch_size, expected_build_rows, device, stream, is_na_equal=is_na_equal,
+                             build_parallel=build_parallel, probe_parallel=probe_parallel, force_broadcast=force_broadcast)
     return JoinState(operator_id, g(build_key_inds), g(probe_key_inds), g(build_colnames), g(probe_colnames), build_outer,
-                     probe_outer, output_batch_size, expected_build_rows, device, stream)
+                     probe_outer, output_batch_size, expected_build_rows, device, stream, is_na_equal=is_na_equal)
 
 
 def join_build_consume_batch(join_state: JoinState, table: Table, is_last: bool):
@@ -83,9 +97,7 @@ def join_build_consume_batch(join_state: JoinState, table: Table, is_last: bool)
         st.build_names = [table.names[i] for i in st.build_indices]
     phys = table.select(st.build_indices)
     if st.handle is None:
-        # the C state needs both schemas; build batches that arrive before the first probe batch are parked
-        st._pending_build.append((phys, bool(is_last)))
-        return bool(is_last), True
+        st._init_c(phys)
     return _feed_build(st, phys, is_last), True
 
 
@@ -102,13 +114,10 @@ def join_probe_consume_batch(join_state: JoinState, table: Table, is_last: bool,
     used_cols = (kept_build_cols, kept_probe_cols) as logical column indices, or None to keep everything."""
     st = join_state
     L = _lib.lib()
-    if st.build_indices is None:
-        raise _lib.B200Error("join_probe_consume_batch called before any build batch")
-    if st.handle is None:
-        st._init_c(table)
-        pend, st._pending_build = st._pending_build, []
-        for phys, last in pend:
-            _feed_build(st, phys, last)
+    if st.build_indices is None or st.handle is None:
+        raise _lib.B200Error("join_probe_consume_batch called before any build batch was consumed")
+    if st.probe_indices is None:
+        st.probe_indices = st._physical(table, st.probe_key_inds)
     phys = table.select(st.probe_indices)
     if used_cols is None:
         kb_logical = sorted(st.build_indices)

@@ -111,6 +111,12 @@ class Column:
     def __post_init__(self):
         if self.length < 0:
             self.length = len(self.data)
+        if isinstance(self.data, np.ndarray) and self.data.dtype.kind in "Mm":
+            # temporal numpy buffers: nanosecond int64 storage, whatever unit they arrive in
+            kind = self.data.dtype.kind
+            if self.c_type < 0:
+                self.c_type = CTypes.DATETIME if kind == "M" else CTypes.TIMEDELTA
+            self.data = np.ascontiguousarray(self.data.astype("datetime64[ns]" if kind == "M" else "timedelta64[ns]", copy=False)).view("int64")
         if self.c_type < 0:
             if isinstance(self.data, np.ndarray):
                 self.c_type = ctype_of(self.data.dtype)
@@ -273,8 +279,11 @@ def column_from_pandas(s) -> Column:
         return column_from_arrow(pa.chunked_array(s.array._pa_array).combine_chunks())
     a = s.to_numpy()
     if a.dtype.kind in "Mm":
+        # DATETIME / TIMEDELTA columns are int64 NANOSECONDS (Bodo_CTypes, _bodo_common.h:331-359): pandas >= 3 hands out
+        # datetime64[us] (and [s]/[ms] on request), so the unit is normalised before the storage is reinterpreted
         ct = CTypes.DATETIME if a.dtype.kind == "M" else CTypes.TIMEDELTA
-        return Column(np.ascontiguousarray(a.astype("int64", copy=False) if a.dtype.itemsize == 8 else a.astype("int64")), None, ct)
+        a = a.astype("datetime64[ns]" if a.dtype.kind == "M" else "timedelta64[ns]", copy=False)
+        return Column(np.ascontiguousarray(a.view("int64")), None, ct)
     if a.dtype == object:
         raise TypeError(f"bodo_b200: column '{s.name}' has object dtype (strings are a 'next' row, SURVEY.md §8f)")
     return Column(np.ascontiguousarray(a), None, ctype_of(a.dtype))

@@ -115,13 +115,16 @@ int64_t b200_groupby_get_metric(void* state, int32_t which);
 /* ---- streaming hash join (reference: bodo/libs/streaming/_join.cpp) ---- */
 
 /* join_state_init_py_entry (_join.cpp:4087-4136). Inner equi-join on the first n_keys (=1) columns;
- * build_table_outer / probe_table_outer select right/left/full-outer semantics. */
+ * build_table_outer / probe_table_outer select right/left/full-outer semantics. `is_na_equal` is the
+ * HashJoinState option of the same name: 0 (what join_state_init_py_entry constructs: NA keys never match,
+ * _join.cpp:3180) or 1 (what bodo/pandas/physical/join.h:267 passes: NA joins NA, pandas merge semantics).
+ * n_probe_arrs may be 0: the probe schema is then taken from the first probe batch. */
 void* b200_join_state_init(int64_t operator_id, const int8_t* build_arr_c_types,
                            const int8_t* build_arr_array_types, int32_t n_build_arrs,
                            const int8_t* probe_arr_c_types, const int8_t* probe_arr_array_types,
                            int32_t n_probe_arrs, uint64_t n_keys, int32_t build_table_outer,
-                           int32_t probe_table_outer, int64_t output_batch_size, int32_t device,
-                           int64_t expected_build_rows, void* stream);
+                           int32_t probe_table_outer, int32_t is_na_equal, int64_t output_batch_size,
+                           int32_t device, int64_t expected_build_rows, void* stream);
 
 /* join_build_consume_batch_py_entry (_join.cpp:4149-4185): appends a build batch; on is_last builds the
  * hash table + CSR groups (JoinPartition::BuildHashTable / FinalizeGroups, _join.cpp:381-512). */
@@ -172,6 +175,9 @@ int b200_merge_segment_bitmaps(const uint8_t* segments, const int64_t* counts, i
 /* ---- helpers for host code that does not link CUDA ---- */
 void* b200_device_malloc(int32_t device, int64_t nbytes);
 void b200_device_free(int32_t device, void* p);
+/* Scratch memory (owner buckets, retry lists, staging) comes from a process-wide, stream-ordered per-device pool that
+ * keeps freed blocks for the next operator state; this returns pooled blocks beyond keep_bytes to the driver. */
+int64_t b200_pool_trim(int32_t device, int64_t keep_bytes);
 int b200_memcpy_d2h(void* dst_host, const void* src_dev, int64_t nbytes, void* stream);
 int b200_memcpy_h2d(void* dst_dev, const void* src_host, int64_t nbytes, void* stream);
 int b200_stream_synchronize(void* stream);

@@ -39,7 +39,8 @@ def test_no_cpu_fallback_without_gpu():
         groupby_build_consume_batch(st, t, True, True)
     from bodo_b200.streaming.join import init_join_state, join_build_consume_batch, join_probe_consume_batch
     js = init_join_state(-1, (0,), (0,), ("a", "b"), ("a", "b"), False, False)
-    join_build_consume_batch(js, t, True)
+    with pytest.raises(B200Error, match="no CUDA device|no CPU fallback|CUDA-only"):
+        join_build_consume_batch(js, t, True)  # build batches go straight to the device: the first one already fails
     with pytest.raises(B200Error):
         join_probe_consume_batch(js, t, True)
 
@@ -51,6 +52,23 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "from oracle" not in txt and "import oracle" not in txt and "libbodo_oracle" not in txt, f
+
+
+def test_temporal_columns_are_nanoseconds_whatever_unit_pandas_hands_out():
+    # pandas >= 3 defaults to datetime64[us]; DATETIME / TIMEDELTA columns are int64 ns (Bodo_CTypes)
+    for unit in ("s", "ms", "us", "ns"):
+        ts = pd.Series(np.array(["2020-01-01T00:00:01", "1999-12-31T23:59:59", "NaT"], dtype=f"datetime64[{unit}]"))
+        td = pd.Series(np.array([1, -5, 86400], dtype=f"timedelta64[{unit}]"))
+        t = Table.from_pandas(pd.DataFrame({"ts": ts, "td": td}))
+        assert [c.c_type for c in t.columns] == [CTypes.DATETIME, CTypes.TIMEDELTA]
+        assert t.columns[0].data[0] == np.datetime64("2020-01-01T00:00:01", "ns").astype("int64")
+        back = t.to_pandas()
+        assert back["ts"][0] == pd.Timestamp("2020-01-01T00:00:01") and back["ts"][1] == pd.Timestamp("1999-12-31T23:59:59")
+        assert pd.isna(back["ts"][2])
+        assert back["td"][2] == pd.Timedelta(86400, unit=unit)
+    from bodo_b200.table import Column
+    c = Column(np.array(["2021-06-01"], dtype="datetime64[D]"))
+    assert c.c_type == CTypes.DATETIME and c.data.dtype == np.int64 and c.data[0] == np.datetime64("2021-06-01", "ns").astype("int64")
 
 
 def test_table_from_pandas_nullable_and_numpy():

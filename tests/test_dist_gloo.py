@@ -43,12 +43,26 @@ def _oracle_partition(table, n_keys, n_pes):
     return Table(cols, list(table.names)), [int(x) for x in counts]
 
 
+def _numpy_merge_bitmaps(bitmap, counts):
+    """Test-only stand-in for b200_merge_segment_bitmaps (per-source byte-padded segments -> one Arrow bitmap)."""
+    bits, off, b = [], 0, bitmap.cpu().numpy()
+    for c in counts:
+        nb = (c + 7) // 8
+        bits.append(np.unpackbits(b[off:off + nb], bitorder="little")[:c])
+        off += nb
+    allbits = np.concatenate(bits) if bits else np.zeros(0, dtype=np.uint8)
+    packed = np.packbits(allbits, bitorder="little")
+    pad = np.zeros((len(packed) + 7) // 8 * 8 + 8, dtype=np.uint8)
+    pad[:len(packed)] = packed
+    return torch.from_numpy(pad)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import pandas as pd
-        from bodo_b200.shuffle import shuffle_table
+        from bodo_b200.shuffle import exchange_table, with_schema_validity
         from bodo_b200.table import Table
         from oracle import oracle as O
         rng = np.random.default_rng(100 + rank)
@@ -56,9 +70,14 @@ def _worker(rank, world, port, q):
         keys = rng.integers(0, 400, n).astype(np.int64)
         df = pd.DataFrame({"k": keys, "v": rng.integers(-9, 9, n).astype(np.int64),
                            "w": pd.array(rng.integers(0, 50, n), dtype="Int64")})
-        df.loc[rng.random(n) < 0.2, "w"] = pd.NA
+        if rank == 0:
+            df.loc[rng.random(n) < 0.2, "w"] = pd.NA  # rank 1 has NO nulls in its nullable column: its bitmap must still travel
         t = Table.from_pandas(df)
-        out = shuffle_table(t, 1, True, partition_fn=_oracle_partition)
+        if rank == 1:  # what an Arrow reader hands over for a chunk without nulls: nullable column, no bitmap
+            from bodo_b200.table import Column
+            t.columns[2] = Column(t.columns[2].data, None, t.columns[2].c_type, t.columns[2].arr_type, t.columns[2].length)
+        part, send_counts = _oracle_partition(with_schema_validity(t), 1, world)
+        out = exchange_table(part, send_counts, merge_bitmaps=_numpy_merge_bitmaps)
         odf = out.to_pandas()
         # 1. every received key belongs to this rank under the reference's hash_to_rank
         dest = O.hash_to_rank(odf["k"].to_numpy(), None, world)

@@ -13,10 +13,10 @@ from tests.helpers import table_to_device
 pytestmark = pytest.mark.gpu
 
 
-def stream_join(build_df, probe_df, build_outer=False, probe_outer=False, batch_size=None, to_device=False, used_cols=None):
+def stream_join(build_df, probe_df, build_outer=False, probe_outer=False, batch_size=None, to_device=False, used_cols=None, is_na_equal=True):
     """Reference-shaped streaming loop (bodo/tests/test_streaming/test_join.py): build batches, then probe batches."""
     bt, pt = Table.from_pandas(build_df), Table.from_pandas(probe_df)
-    st = init_join_state(-1, (0,), (0,), tuple(build_df.columns), tuple(probe_df.columns), build_outer, probe_outer)
+    st = init_join_state(-1, (0,), (0,), tuple(build_df.columns), tuple(probe_df.columns), build_outer, probe_outer, is_na_equal=is_na_equal)
     bs = batch_size or max(bt.n_rows, pt.n_rows, 1)
     it, last = 0, False
     while not last:
@@ -35,14 +35,14 @@ def stream_join(build_df, probe_df, build_outer=False, probe_outer=False, batch_
     return pd.concat(outs, ignore_index=True)
 
 
-def oracle_join_frame(oracle, build_df, probe_df, build_outer=False, probe_outer=False):
+def oracle_join_frame(oracle, build_df, probe_df, build_outer=False, probe_outer=False, is_na_equal=True):
     def kv(s):
         if hasattr(s.array, "_mask"):
             return np.asarray(s.array._data, dtype=np.int64), ~np.asarray(s.array._mask)
         return s.to_numpy(dtype=np.int64), None
     bk, bv = kv(build_df.iloc[:, 0])
     pk, pv = kv(probe_df.iloc[:, 0])
-    bi, pi = oracle.hash_join(bk, bv, pk, pv, build_outer, probe_outer, True)
+    bi, pi = oracle.hash_join(bk, bv, pk, pv, build_outer, probe_outer, is_na_equal)
     out = {}
     for name in build_df.columns:
         col = build_df[name].astype("Float64" if build_df[name].dtype.kind == "f" else "Int64")
@@ -128,3 +128,17 @@ def test_synthetic_join_vs_oracle(gpu_lib, oracle):
     # kept columns: drop the probe key and b2
     got2 = stream_join(build, probe, batch_size=300_000, to_device=True, used_cols=([0, 1], [1, 2]))
     assert_rowset_equal(got2, exp.iloc[:, [0, 1, 4, 5]])
+
+
+@pytest.mark.parametrize("build_outer,probe_outer", [(False, False), (True, True), (True, False), (False, True)])
+def test_na_keys_never_match_on_the_streaming_door(gpu_lib, oracle, build_outer, probe_outer):
+    # is_na_equal=False is what join_state_init_py_entry constructs (bodo/libs/streaming/_join.cpp:4087-4136, NA build keys
+    # filtered at :3180): NA keys match nothing and survive only as NULL-extended rows of an outer side
+    build = pd.DataFrame({"A": pd.array([2, None, 3, None, 7], dtype="Int64"), "B": [1.5, 2.5, 3.5, 4.5, 5.5]})
+    probe = pd.DataFrame({"C": pd.array([2, 3, None, 8, None, 2], dtype="Int64"), "D": pd.array([10, None, 30, 40, 50, 60], dtype="Int64")})
+    got = stream_join(build, probe, build_outer, probe_outer, batch_size=2, is_na_equal=False)
+    exp = oracle_join_frame(oracle, build, probe, build_outer, probe_outer, is_na_equal=False)
+    assert_rowset_equal(got, exp)
+    n_inner = 3  # 2-2, 2-2 (probe has two 2s), 3-3
+    n_exp = n_inner + (3 if build_outer else 0) + (3 if probe_outer else 0)  # unmatched: build {NA, NA, 7}, probe {NA, 8, NA}
+    assert len(got) == n_exp
