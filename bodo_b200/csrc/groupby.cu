@@ -1277,6 +1277,8 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     }
 }
 
+#include "spf.cuh"  // SPF: the fused persistent variant of the SM-partitioned path (one kernel, bucket hand-off through L2)
+
 // ---- low-cardinality kernel (LC): every CTA keeps a private shared-memory table of ALL groups ----------------
 // Used when the (estimated) number of groups fits one CTA's table (<= LC_SLOTS / 2), e.g. BASELINE.json configs[0]
 // (20 M rows, 30 groups) where every row of a warp hits one of a handful of hot keys.  Rows are pre-aggregated inside
