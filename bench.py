@@ -247,6 +247,7 @@ def main():
             stats["n_out"] = out.n_rows
             stats["sum_of_sums"] = int(cols[1].sum().item()) if out.n_rows else 0
             stats["sum_of_counts"] = int(cols[2].sum().item()) if out.n_rows else 0
+            stats["per_group"] = per_group_check(cols, out.n_rows)
             stats["launches"] = G.get_metric(st, 4)
             if profile:
                 stats["consume_us"] = G.get_metric(st, 6)
@@ -259,6 +260,40 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def per_group_check(cols, n_out):
+        """EVERY group this rank produced against an independent recomputation (torch scatter-adds over the raw rows of all
+        ranks, dense by key: the synthetic keys are 0 .. groups-1), and its placement: hash_to_rank(key) == rank — the
+        reference's ownership rule (bodo/libs/_shuffle.h:5-7).  Returns (ok, n_bad, n_misplaced, n_groups_expected_total)."""
+        ref_sum = torch.zeros(args.groups, dtype=torch.int64, device=dev)
+        ref_cnt = torch.zeros(args.groups, dtype=torch.int64, device=dev)
+        step_rows = 1 << 27
+        for r0 in range(0, n_local, step_rows):  # bounded temporaries
+            kk = keys[r0:r0 + step_rows]
+            ref_sum.index_add_(0, kk, vals[r0:r0 + step_rows])
+            ref_cnt += torch.bincount(kk, minlength=args.groups)
+        if world > 1:
+            dist.all_reduce(ref_sum)
+            dist.all_reduce(ref_cnt)
+        n_expected = int((ref_cnt > 0).sum().item())
+        if n_out == 0:
+            return True, 0, 0, n_expected
+        okeys = cols[0][:n_out]
+        in_range = (okeys >= 0) & (okeys < args.groups)
+        safe = torch.where(in_range, okeys, torch.zeros_like(okeys))
+        bad = (~in_range) | (cols[1][:n_out] != ref_sum[safe]) | (cols[2][:n_out] != ref_cnt[safe])
+        dup = okeys.numel() - torch.unique(okeys).numel()
+        n_misplaced = 0
+        if world > 1:
+            dest = torch.empty(n_out, dtype=torch.int32, device=dev)
+            from bodo_b200.table import CTable
+            ct = CTable(Table([Column(okeys.contiguous())], ["key"]))
+            _lib.check(_lib.lib().b200_hash_to_rank(ct.ptr, world, _lib.ffi.cast("int32_t*", dest.data_ptr()), _lib.ffi.cast("void*", stream_ptr)),
+                       "hash_to_rank")
+            torch.cuda.synchronize(dev)
+            n_misplaced = int((dest != rank).sum().item())
+        n_bad = int(bad.sum().item()) + dup
+        return (n_bad == 0 and n_misplaced == 0), n_bad, n_misplaced, n_expected
 
     for _ in range(max(args.warmup, 0)):
         one_step(table)
@@ -277,7 +312,8 @@ def main():
     # untimed: one profiled step (per-launch CUDA events inside the library) + result check
     one_step(table, collect=True, profile=True)
     barrier()
-    tot = torch.tensor([ms, float(stats["n_out"]), 0.0], dtype=torch.float64, device=dev)
+    pg_ok, pg_bad, pg_misplaced, pg_expected = stats["per_group"]
+    tot = torch.tensor([ms, float(stats["n_out"]), float(pg_bad + pg_misplaced)], dtype=torch.float64, device=dev)
     chk = torch.tensor([stats["sum_of_sums"], stats["sum_of_counts"], expect_sum], dtype=torch.int64, device=dev)
     if world > 1:
         mx = tot.clone()
@@ -286,7 +322,8 @@ def main():
         dist.all_reduce(chk, op=dist.ReduceOp.SUM)
         ms = float(mx[0].item())
     n_groups_total = int(tot[1].item())
-    check_ok = int(chk[1].item()) == args.rows and int(chk[0].item()) == int(chk[2].item())
+    per_group_ok = int(tot[2].item()) == 0 and n_groups_total == pg_expected
+    check_ok = int(chk[1].item()) == args.rows and int(chk[0].item()) == int(chk[2].item()) and per_group_ok
 
     value = args.rows * args.steps / (ms * 1e-3)
     peak, peak_kind = peaks()
@@ -354,7 +391,8 @@ def main():
             "config": {"workload": workload_name(args), "rows": args.rows, "groups": args.groups, "aggs": ["sum", "count"],
                        "rows_per_gpu": n_local, "l2": "inputs (16 B/row x rows_per_gpu) exceed the 126 MB L2; no flush needed",
                        "step": "init state + consume + exchange + finalize + produce", "result_groups": n_groups_total,
-                       "result_check": "ok" if check_ok else "MISMATCH"},
+                       "result_check": ("per-group ok: every group's SUM and COUNT equal an independent device recomputation over all ranks' rows"
+                                        + ("; every group sits on hash_to_rank(key)" if world > 1 else "")) if check_ok else "MISMATCH"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(stats.get("launches", 0)) * args.steps,
         }

@@ -294,3 +294,30 @@ def test_multi_key_groupby_vs_pandas(gpu_lib, dropna):
         np.testing.assert_array_equal(g[c].to_numpy(), e[c].to_numpy(), err_msg=c)
     for c in ("f2", "f3"):
         np.testing.assert_allclose(g[c].to_numpy(), e[c].to_numpy(), rtol=1e-5, atol=1e-8, err_msg=c)
+
+
+def test_float32_sum_mean_stated_tolerance(gpu_lib, oracle):
+    """float32 SUM: the reference accumulates in float32 (aggfunc<float, sum>, bodo/libs/groupby/_groupby_agg_funcs.h:159-173,
+    in batch / combine order); the device accumulates every group in float64 (atomics reorder additions, so a float32
+    accumulator would not be reproducible anyway) and narrows once at eval.  The two differ by float32 rounding of the
+    running sum: |device - reference| <= n_g * 2^-24 * sum|v| per group — the bound asserted here, with the oracle
+    (float32 accumulation in the reference's order) as the reference value.  Against the exact (float64) sum the device
+    result is within ONE float32 rounding, i.e. it is the more accurate of the two."""
+    rng = np.random.default_rng(17)
+    n, ng = 200_000, 97
+    k = rng.integers(0, ng, n).astype(np.int64)
+    v = (rng.random(n) * 100.0 - 20.0).astype(np.float32)
+    df = pd.DataFrame({"k": k, "v": v})
+    t = Table.from_pandas(df)
+    got = positional(stream_groupby(t, (0,), ("sum", "mean", "count"), (0, 1, 2, 3), (1, 1, 1), batch_size=4096, to_device=True))
+    got = got.sort_values("key").reset_index(drop=True)
+    assert got["f0"].dtype == np.float32  # SUM(float32) stays float32 (get_groupby_output_dtype, _groupby_common.cpp:567-619)
+    exp = oracle_groupby_frame(oracle, t, 0, ["sum", "mean", "count"], [1, 1, 1], batch_size=4096).sort_values("key").reset_index(drop=True)
+    g64 = df.assign(v=df.v.astype(np.float64)).groupby("k").v
+    exact, cnt, abs_sum = g64.sum().to_numpy(), g64.count().to_numpy(), g64.apply(lambda s: s.abs().sum()).to_numpy()
+    np.testing.assert_array_equal(got["f2"].to_numpy(), cnt)
+    bound_ref = cnt * 2.0 ** -24 * abs_sum
+    assert (np.abs(got["f0"].to_numpy().astype(np.float64) - exp["f0"].to_numpy().astype(np.float64)) <= bound_ref).all()
+    # one float32 rounding of the exact sum
+    assert (np.abs(got["f0"].to_numpy().astype(np.float64) - exact) <= 2.0 ** -24 * np.abs(exact) * 1.0000001).all()
+    np.testing.assert_allclose(got["f1"].to_numpy(), exact / cnt, rtol=1e-12)  # MEAN is float64 throughout (mean_agg :673-689)
