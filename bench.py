@@ -54,6 +54,13 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000_000)
     ap.add_argument("--ref-sample-rows", type=int, default=512_000_000)
+    # --workload join: BASELINE.json configs[2] (benchmarks/join_bench.py); the default workload is the contract's configs[1] / [3]
+    ap.add_argument("--workload", default="groupby", choices=["groupby", "join"])
+    ap.add_argument("--build-rows", type=int, default=100_000_000)
+    ap.add_argument("--probe-rows", type=int, default=1_000_000_000)
+    ap.add_argument("--probe-batch", type=int, default=250_000_000)
+    ap.add_argument("--sample-lo", type=int, default=1000, help="join parity: sorted row-set equality for keys in [lo, hi)")
+    ap.add_argument("--sample-hi", type=int, default=1400)
     return ap.parse_args()
 
 
@@ -190,6 +197,11 @@ def workload_name(args):
 
 def main():
     args = parse_args()
+    if args.workload == "join":
+        from benchmarks import join_bench
+
+        join_bench.run(args, ClockSampler, peaks)
+        return
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -295,10 +307,12 @@ def main():
         n_bad = int(bad.sum().item()) + dup
         return (n_bad == 0 and n_misplaced == 0), n_bad, n_misplaced, n_expected
 
+    # the clock sampler starts before the warm-up (nvidia-smi needs ~0.2 s to deliver its first sample and a short timed region
+    # would otherwise end before it): warm-up and timed steps are the same workload, every sample is taken under load
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 0)):
         one_step(table)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
