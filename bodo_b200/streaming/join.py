@@ -89,6 +89,8 @@ def init_join_state(operator_id, build_key_inds, probe_key_inds, build_colnames,
 
 def join_build_consume_batch(join_state: JoinState, table: Table, is_last: bool):
     """Mirror of join_build_consume_batch (join.py:1270-1330): returns (is_last, request_input)."""
+    if hasattr(join_state, "build_consume"):  # sharded state (build_parallel / probe_parallel): dist_join.DistJoinState
+        return join_state.build_consume(table, is_last)
     st = join_state
     if st.build_indices is None:
         st.build_indices = st._physical(table, st.build_key_inds)
@@ -112,6 +114,8 @@ def _feed_build(st: JoinState, phys: Table, is_last: bool) -> bool:
 def join_probe_consume_batch(join_state: JoinState, table: Table, is_last: bool, produce_output: bool = True, used_cols=None):
     """Mirror of join_probe_consume_batch (join.py:1838-1950): returns (out_table, is_last, request_input).
     used_cols = (kept_build_cols, kept_probe_cols) as logical column indices, or None to keep everything."""
+    if hasattr(join_state, "probe_consume"):
+        return join_state.probe_consume(table, is_last, produce_output, used_cols)
     st = join_state
     L = _lib.lib()
     if st.build_indices is None or st.handle is None:
@@ -149,10 +153,12 @@ def join_probe_consume_batch(join_state: JoinState, table: Table, is_last: bool,
 
 
 def delete_join_state(join_state: JoinState) -> None:
+    join_state = getattr(join_state, "local", join_state)
     if join_state.handle is not None:
         _lib.lib().b200_delete_join_state(join_state.handle)
         join_state.handle = None
 
 
 def get_metric(join_state: JoinState, which: int) -> int:
+    join_state = getattr(join_state, "local", join_state)
     return int(_lib.lib().b200_join_get_metric(join_state.handle, which))

@@ -91,3 +91,102 @@ def test_sharded_groupby_and_shuffle_nccl(gpu_lib):
         p.join(timeout=60)
     for r in sorted(res, key=lambda x: x[0]):
         assert len(r) == 6 and all(r[1:]), r
+
+
+def _join_worker(rank, world, port, q):
+    import pandas as pd
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from bodo_b200.streaming.join import (delete_join_state, init_join_state, join_build_consume_batch,
+                                              join_probe_consume_batch)
+        from bodo_b200.table import Table
+        from oracle import oracle as O
+        rng = np.random.default_rng(77)  # same global tables on every rank; each rank feeds its own row slice
+        nb, npr = 40_000, 150_000
+        build = pd.DataFrame({"k": rng.integers(0, 30_000, nb).astype(np.int64), "b1": rng.integers(0, 1 << 40, nb),
+                              "b2": pd.array(rng.integers(0, 100, nb), dtype="Int64")})
+        build.loc[rng.random(nb) < 0.1, "b2"] = pd.NA
+        probe = pd.DataFrame({"k": rng.integers(0, 45_000, npr).astype(np.int64), "p1": rng.random(npr)})
+        results = {}
+        for name, kw, bo, po in (("shuffle", {}, False, False), ("shuffle-outer", {}, True, True),
+                                 ("broadcast", {"force_broadcast": True}, False, True)):
+            os.environ["BODO_BCAST_JOIN_THRESHOLD"] = "0" if name != "broadcast" else str(10 << 20)  # 0: never broadcast on size
+            st = init_join_state(-1, (0,), (0,), tuple(build.columns), tuple(probe.columns), bo, po, build_parallel=True,
+                                 probe_parallel=True, device=rank, is_na_equal=True, **kw)
+            bchunk, pchunk = (nb + world - 1) // world, (npr + world - 1) // world
+            mb = build.iloc[rank * bchunk:(rank + 1) * bchunk]
+            mp_ = probe.iloc[rank * pchunk:(rank + 1) * pchunk]
+            half = len(mb) // 2
+            join_build_consume_batch(st, Table.from_pandas(mb.iloc[:half]), False)
+            join_build_consume_batch(st, Table.from_pandas(mb.iloc[half:]), True)
+            outs = []
+            cuts = [0, len(mp_) // 3, len(mp_)]
+            for b in range(2):
+                out, _, _ = join_probe_consume_batch(st, Table.from_pandas(mp_.iloc[cuts[b]:cuts[b + 1]]), b == 1, True)
+                outs.append(out.to_pandas())
+            met = dict(st.metrics)
+            delete_join_state(st)
+            got = pd.concat(outs, ignore_index=True)
+            # global check: gather every rank's output rows, compare the multiset with the oracle join of the global tables
+            allg = [None] * world
+            dist.all_gather_object(allg, got)
+            allm = [None] * world
+            dist.all_gather_object(allm, met)
+            if rank == 0:
+                g = pd.concat(allg, ignore_index=True)
+                bi, pi = O.hash_join(build.k.to_numpy(), None, probe.k.to_numpy(), None, bo, po, True)
+                def take(df, idx):
+                    out = {}
+                    for c in df.columns:
+                        col = df[c].astype("Float64" if df[c].dtype.kind == "f" else "Int64").take(np.where(idx >= 0, idx, 0)).reset_index(drop=True)
+                        col[idx < 0] = pd.NA
+                        out[c] = col
+                    return out
+                e = pd.DataFrame({**{f"b_{c}": v for c, v in take(build, bi).items()}, **{f"p_{c}": v for c, v in take(probe, pi).items()}})
+                def canon(df):
+                    df = df.copy(); df.columns = [f"c{i}" for i in range(df.shape[1])]
+                    for c in df.columns:
+                        df[c] = df[c].to_numpy(dtype="float64", na_value=np.nan)
+                    return df.sort_values(list(df.columns), na_position="last").reset_index(drop=True)
+                cg, ce = canon(g), canon(e)
+                ok = cg.shape == ce.shape and bool(np.array_equal(cg.to_numpy(), ce.to_numpy(), equal_nan=True))
+                bcast = [m["broadcast"] for m in allm]
+                moved = sum(m["build_rows_local"] for m in allm)
+                results[name] = (ok, bcast, moved)
+        q.put((rank, results))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_join_shuffle_and_broadcast_nccl(gpu_lib):
+    """build_parallel / probe_parallel (bodo/libs/streaming/_join.cpp:3243-3405): rows go to hash_to_rank(key) — or the build side
+    is all-gathered (broadcast join) — and the union of the ranks' outputs equals the oracle's join of the global tables."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_join_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    r0 = [r for r in res if r[0] == 0][0]
+    assert isinstance(r0[1], dict), r0
+    for r in res:
+        assert isinstance(r[1], dict), r
+    ok, bcast, moved = r0[1]["shuffle"]
+    assert ok and bcast == [0] * world and moved == 40_000, r0  # partitioned: every build row lives on exactly one rank
+    ok, bcast, moved = r0[1]["shuffle-outer"]
+    assert ok and bcast == [0] * world, r0
+    ok, bcast, moved = r0[1]["broadcast"]
+    assert ok and bcast == [1] * world and moved == 40_000 * world, r0  # broadcast: every rank holds the whole build table
