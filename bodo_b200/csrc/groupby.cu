@@ -248,15 +248,23 @@ __global__ void rehash_kernel(const __grid_constant__ RehashArgs a) {
 }
 
 // ---- finalize: compact occupied slots, then evaluate output columns ----
+// n_pes > 1: only the groups this rank OWNS (hash_to_rank(key) == rank) are output — after the fused exchange the table still
+// holds the partial aggregates of groups that were sent to their owners (they are never touched again: received rows only
+// carry keys this rank owns)
 __global__ void compact_slots_kernel(const long long* __restrict__ tkeys, uint64_t cap, const long long* counters,
-                                     long long* cursor, uint64_t* slot_of_out) {
+                                     long long* cursor, uint64_t* slot_of_out, int n_pes, int rank) {
     const bool na_present = counters[3] != 0, empty_present = counters[4] != 0;
+    const uint32_t na_hash = (uint32_t)xxh3_64_short(1ull, 8, SEED_HASH_PARTITION);  // hash_na_val (_array_hash.cpp:22-29)
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t s0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s0 < ((cap + 2 + 31) & ~31ull); s0 += stride) {
         bool occ = false;
         if (s0 < cap) occ = tkeys[s0] != EMPTY_KEY;
         else if (s0 == cap) occ = na_present;
         else if (s0 == cap + 1) occ = empty_present;
+        if (occ && n_pes > 1) {
+            const uint32_t h = s0 == cap ? na_hash : (uint32_t)key_hash(s0 < cap ? tkeys[s0] : EMPTY_KEY);
+            occ = hash_to_rank_u32(h, n_pes) == rank;
+        }
         unsigned m = __ballot_sync(0xffffffffu, occ);
         int lane = threadIdx.x & 31;
         long long base = 0;
@@ -417,10 +425,8 @@ struct CombineArgs {
     void* a1[MAX_OPS];
 };
 // combine step (get_combine_func, groupby/_groupby_update.cpp:41-57): count/size/mean -> sum, min -> min, max -> max
-__global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_rows; i += stride) {
-        int64_t row = a.index_list ? (int64_t)a.index_list[i] : i;
+__device__ __forceinline__ void combine_one_row(const CombineArgs& a, int64_t row) {
+    {
         const unsigned long long* r = a.in + row * a.row_words;
         long long key = (long long)r[0];
         bool kvalid = r[1] & 1;
@@ -432,7 +438,7 @@ __global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
             if (slot == ~0ull) {
                 unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
                 a.fail_list[f] = (uint32_t)row;
-                continue;
+                return;
             }
         }
         int w = 2;
@@ -453,6 +459,84 @@ __global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
             }
             if (a.a1[j] && a.kinds[j] != K_MEAN) atomicAdd((unsigned long long*)a.a1[j] + slot, v1);
         }
+    }
+}
+__global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_rows; i += stride)
+        combine_one_row(a, a.index_list ? (int64_t)a.index_list[i] : i);
+}
+
+// ---- fused exchange: pack + all-to-all in ONE kernel over peer memory (NVLink stores), combine straight out of the slab ----
+// Every rank owns a receive slab in symmetric memory (mapped into every peer's address space): a header of n_pes counts
+// followed by n_pes segments of cap_rows partial rows, segment s written by rank s.  xchg_pack_remote_kernel walks the local
+// table once and stores every group that another rank owns straight into that owner's slab (no send buffer, no count
+// exchange, no host round trip); xchg_post_counts_kernel then tells every peer how many rows it got; after a device-side
+// barrier across the ranks, xchg_combine_slab_kernel merges the received rows into the local table.  A sender whose share for
+// some destination exceeds cap_rows flags that in EVERY peer's header; then no rank combines and the host falls back to the
+// NCCL exchange (the local tables are still intact).
+constexpr unsigned long long XCHG_OVERFLOW = 1ull << 63;
+constexpr int XCHG_HDR_BYTES = 256;
+struct XchgPackArgs {
+    const long long* tkeys;
+    uint64_t cap;
+    const long long* counters;
+    int n_pes, rank;
+    int n_acc;
+    const unsigned long long* acc[2 * MAX_OPS];
+    int row_words;
+    unsigned long long* cursors;      // [n_pes] rows packed per destination (device)
+    void* const* peer_slabs;          // [n_pes] device pointers to every rank's slab (own slab included)
+    long long cap_rows;
+};
+__global__ void xchg_pack_remote_kernel(const __grid_constant__ XchgPackArgs a) {
+    const bool na_present = a.counters[3] != 0, empty_present = a.counters[4] != 0;
+    const uint32_t na_hash = (uint32_t)xxh3_64_short(1ull, 8, SEED_HASH_PARTITION);
+    const int lane = threadIdx.x & 31;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < ((a.cap + 2 + 31) & ~31ull); s += stride) {
+        bool occ = false;
+        if (s < a.cap) occ = a.tkeys[s] != EMPTY_KEY;
+        else if (s == a.cap) occ = na_present;
+        else if (s == a.cap + 1) occ = empty_present;
+        const long long key = s < a.cap ? (occ ? a.tkeys[s] : 0) : (s == a.cap ? 0 : EMPTY_KEY);
+        const bool kvalid = s != a.cap;
+        const uint32_t h = kvalid ? (uint32_t)key_hash(key) : na_hash;
+        int d = occ ? hash_to_rank_u32(h, a.n_pes) : -1;
+        if (d == a.rank) d = -1;  // owned here: stays in the table
+        // warp-aggregated cursor: one atomic per (warp, destination)
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        const int rank_in_peers = __popc(peers & ((1u << lane) - 1));
+        unsigned long long base = 0;
+        if (d >= 0 && lane == leader) base = atomicAdd(&a.cursors[d], (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (d >= 0) {
+            const unsigned long long pos = base + rank_in_peers;
+            if (pos < (unsigned long long)a.cap_rows) {
+                unsigned long long* o = (unsigned long long*)((char*)a.peer_slabs[d] + XCHG_HDR_BYTES) + ((size_t)a.rank * a.cap_rows + pos) * a.row_words;
+                o[0] = (unsigned long long)key;
+                o[1] = kvalid ? 1ull : 0ull;
+                for (int j = 0; j < a.n_acc; j++) o[2 + j] = a.acc[j][s];
+            }
+        }
+    }
+}
+__global__ void xchg_post_counts_kernel(const unsigned long long* cursors, void* const* peer_slabs, int n_pes, int rank, long long cap_rows) {
+    const int d = threadIdx.x;
+    const unsigned long long c = d < n_pes ? cursors[d] : 0ull;
+    const bool any_over = __any_sync(0xffffffffu, c > (unsigned long long)cap_rows);
+    if (d < n_pes) ((unsigned long long*)peer_slabs[d])[rank] = (c > (unsigned long long)cap_rows ? (unsigned long long)cap_rows : c) | (any_over ? XCHG_OVERFLOW : 0ull);
+}
+__global__ void xchg_combine_slab_kernel(const __grid_constant__ CombineArgs a, const unsigned long long* hdr, int n_pes, long long cap_rows) {
+    // a.in = first row of segment 0; flat row index = source * cap_rows + r (also what the fail list records)
+    bool over = false;
+    for (int s = 0; s < n_pes; s++) over |= (hdr[s] & XCHG_OVERFLOW) != 0;
+    if (over) { if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[7] = 1; return; }  // every rank sees the same flags: nobody combines
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int s = 0; s < n_pes; s++) {
+        const int64_t n = (int64_t)(hdr[s] & ~XCHG_OVERFLOW);
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) combine_one_row(a, (int64_t)s * cap_rows + i);
     }
 }
 
@@ -2123,17 +2207,19 @@ class GroupbyState {
     }
 
     // ---- finalize ----
-    void compact() {
-        read_counters();
-        n_groups_bound = n_groups + untracked_groups;
-        int64_t max_out = n_groups_bound + 2;
+    // Compacts the occupied slots (owned_only: of the groups this rank owns).  No host synchronisation: the output is sized by
+    // the table's group limit (cap / 2 + the two special slots), the count stays on the device (counters[2]).
+    int64_t max_out_bound() const { return (int64_t)(cap / 2) + 2; }
+    void compact(bool owned_only = false) {
+        int64_t max_out = max_out_bound();
         d_slot_of_out.ensure((size_t)max_out * 8);
         B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 16, 0, 8, stream));
         if (nk > 1)
             compact_mk_kernel<<<grid_for((int64_t)cap), 256, 0, stream>>>(d_tags.as<unsigned long long>(), cap, d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>());
         else
             compact_slots_kernel<<<grid_for((int64_t)cap + 2), 256, 0, stream>>>(d_keys.as<long long>(), cap, d_counters.as<long long>(),
-                                                                                      d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>());
+                                                                                      d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>(),
+                                                                                      owned_only ? n_pes : 1, rank);
         launches++;
         B200_CUDA(cudaGetLastError());
         n_out = -1;  // known on the device (counters[2]); the host learns it with the next counter read-back
@@ -2144,8 +2230,8 @@ class GroupbyState {
         double tf0 = now();
         struct Acc3 { double& t; double t0; ~Acc3() { t += now() - t0; } } acc3{t_finalize, tf0};
         B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
-        compact();
-        const int64_t max_out = n_groups_bound + 2;  // group count (+ the two special slots) from compact()'s read-back
+        compact(/*owned_only=*/parallel && n_pes > 1);
+        const int64_t max_out = max_out_bound();
         EvalArgs e{};
         e.tkeys = nk == 1 ? d_keys.as<long long>() : nullptr; e.cap = cap; e.slot_of_out = d_slot_of_out.as<uint64_t>(); e.n_out_ptr = d_counters.as<long long>() + 2;
         e.key_ctype = c_types[0];
@@ -2179,10 +2265,81 @@ class GroupbyState {
         launches++;
         B200_CUDA(cudaGetLastError());
         read_counters();  // one synchronisation: the output is complete and n_out is known
+        if (xchg_fused) {
+            if (h_counters[7] != 0) {  // some rank's share did not fit its slab segment: nobody combined, the NCCL exchange takes over
+                B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 56, 0, 8, stream));
+                xchg_fused = false;
+                return -2;
+            }
+            if (h_counters[1] > 0) {
+                // received rows that found the table at its group limit: grow, merge them from the slab (still intact), evaluate again
+                int64_t nf = h_counters[1];
+                fail_rows += nf;
+                uint64_t nc = cap;
+                while (nc < 2ull * (uint64_t)(n_groups + nf)) nc <<= 1;
+                if (nc == cap) nc <<= 1;
+                grow(nc);
+                DevBuf replay_list;
+                replay_list.alloc((size_t)nf * 4);
+                B200_CUDA(cudaMemcpyAsync(replay_list.p, d_fail.p, (size_t)nf * 4, cudaMemcpyDeviceToDevice, stream));
+                B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8, 0, 8, stream));
+                CombineArgs c = combine_args((const unsigned long long*)((const char*)xchg_slab + XCHG_HDR_BYTES), nf, /*group_limit=*/-1);
+                c.index_list = replay_list.as<uint32_t>();
+                combine_partials_kernel<<<grid_for(nf), 256, 0, stream>>>(c);
+                launches++;
+                B200_CUDA(cudaGetLastError());
+                B200_CUDA(cudaStreamSynchronize(stream));
+                return finalize();
+            }
+        }
         n_out = h_counters[2];
         finalized = true;
         out_cursor = 0;
         return n_out;
+    }
+
+    // ---- fused exchange (see xchg_pack_remote_kernel) ----
+    bool xchg_fused = false;
+    const void* xchg_slab = nullptr;
+    DevBuf d_xchg_cursors;
+    CombineArgs combine_args(const unsigned long long* in, int64_t n_rows, long long group_limit) {
+        CombineArgs c{};
+        c.in = in; c.n_rows = n_rows; c.row_words = 2 + acc_count();
+        c.tkeys = d_keys.as<long long>(); c.cap = cap; c.counters = d_counters.as<long long>(); c.group_limit = group_limit;
+        c.fail_list = d_fail.as<uint32_t>(); c.index_list = nullptr; c.n_ops = n_funcs;
+        for (int j = 0; j < n_funcs; j++) { c.kinds[j] = funcs[j].kind; c.a0[j] = d_a0[j].p; c.a1[j] = funcs[j].has_a1 ? d_a1[j].p : nullptr; }
+        return c;
+    }
+    int64_t xchg_row_bytes() const { return (int64_t)(2 + acc_count()) * 8; }
+    void exchange_fused_pack(void* const* peer_slabs_dev, int64_t cap_rows) {
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
+        B200_REQUIRE(nk == 1, "b200 groupby: the fused exchange handles single-column keys");
+        build_done = true;
+        d_xchg_cursors.ensure((size_t)std::max(n_pes, 32) * 8);
+        B200_CUDA(cudaMemsetAsync(d_xchg_cursors.p, 0, (size_t)std::max(n_pes, 32) * 8, stream));
+        XchgPackArgs p{};
+        p.tkeys = d_keys.as<long long>(); p.cap = cap; p.counters = d_counters.as<long long>(); p.n_pes = n_pes; p.rank = rank;
+        int n = 0;
+        for (int j = 0; j < n_funcs; j++) {
+            p.acc[n++] = d_a0[j].as<unsigned long long>();
+            if (funcs[j].has_a1) p.acc[n++] = d_a1[j].as<unsigned long long>();
+        }
+        p.n_acc = n; p.row_words = 2 + n; p.cursors = d_xchg_cursors.as<unsigned long long>(); p.peer_slabs = peer_slabs_dev; p.cap_rows = cap_rows;
+        xchg_pack_remote_kernel<<<grid_for((int64_t)cap + 2), 256, 0, stream>>>(p);
+        xchg_post_counts_kernel<<<1, 32, 0, stream>>>(d_xchg_cursors.as<unsigned long long>(), peer_slabs_dev, n_pes, rank, cap_rows);
+        launches += 2;
+        B200_CUDA(cudaGetLastError());
+    }
+    void exchange_fused_combine(const void* my_slab, int64_t cap_rows) {
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
+        d_fail.ensure(device, (size_t)n_pes * (size_t)cap_rows * 4);
+        CombineArgs c = combine_args((const unsigned long long*)((const char*)my_slab + XCHG_HDR_BYTES), 0, (long long)(cap / 2));
+        xchg_combine_slab_kernel<<<grid_for(std::min<int64_t>(cap_rows, 1 << 22)), 256, 0, stream>>>(c, (const unsigned long long*)my_slab, n_pes, cap_rows);
+        launches++;
+        B200_CUDA(cudaGetLastError());
+        xchg_fused = true;
+        xchg_slab = my_slab;
+        untracked_groups = 0;
     }
 
     int acc_count() const { int n = 0; for (auto& f : funcs) n += f.has_a1 ? 2 : 1; return n; }
@@ -2191,7 +2348,7 @@ class GroupbyState {
     int64_t shuffle_prepare(int64_t* send_counts) {
         B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         build_done = true;
-        compact();
+        compact(/*owned_only=*/false);
         read_counters();
         n_out = h_counters[2];
         d_dest_count.ensure((size_t)n_pes * 8);
@@ -2258,7 +2415,8 @@ class GroupbyState {
     }
 
     int produce(b200_table* out, int32_t* out_is_last, bool produce_output) {
-        if (!finalized) finalize();
+        if (!finalized && finalize() == -2)
+            throw Error("b200 groupby: the fused exchange overflowed its slab; run the prepare/pack/combine exchange and finalize again before producing output");
         int64_t bs = output_batch_size > 0 ? output_batch_size : n_out;
         if (bs % 32 != 0 && bs < n_out) bs = (bs + 31) & ~31ll;  // validity bitmaps are sliced at word granularity
         int64_t rows = produce_output ? std::min(bs, n_out - out_cursor) : 0;
@@ -2341,6 +2499,21 @@ int64_t b200_groupby_shuffle_send_bytes(void* state) {
 int b200_groupby_shuffle_pack(void* state, void* send_buf) {
     B200_TRY
     ((GroupbyState*)state)->shuffle_pack(send_buf);
+    return 0;
+    B200_CATCH(-1)
+}
+int64_t b200_groupby_exchange_row_bytes(void* state) { return ((GroupbyState*)state)->xchg_row_bytes(); }
+int b200_groupby_exchange_fused_pack(void* state, void* const* peer_slabs_dev, int64_t cap_rows) {
+    B200_TRY
+    B200_REQUIRE(state && peer_slabs_dev && cap_rows > 0, "b200 groupby: bad fused-exchange arguments");
+    ((GroupbyState*)state)->exchange_fused_pack(peer_slabs_dev, cap_rows);
+    return 0;
+    B200_CATCH(-1)
+}
+int b200_groupby_exchange_fused_combine(void* state, const void* my_slab, int64_t cap_rows) {
+    B200_TRY
+    B200_REQUIRE(state && my_slab && cap_rows > 0, "b200 groupby: bad fused-exchange arguments");
+    ((GroupbyState*)state)->exchange_fused_combine(my_slab, cap_rows);
     return 0;
     B200_CATCH(-1)
 }

@@ -102,7 +102,50 @@ class GroupbyState:
         self.out_names = key_names + uniq
 
     def _exchange(self):
-        """Hash-partition exchange of the partial aggregates (one all-to-all-v), then combine."""
+        """Hash-partition exchange of the partial aggregates after the last local batch, then finalize.
+
+        Fused form (default): ONE kernel packs every partial row another rank owns straight into that rank's receive slab over
+        NVLink (symmetric memory, streaming/exchange.py), a device-side barrier, one combine kernel — no count exchange, no
+        send buffer, no host synchronisation before finalize.  Falls back to the NCCL all-to-all-v (`_exchange_nccl`) when
+        symmetric memory is unavailable or a rank's share did not fit its slab segment (finalize reports that: -2)."""
+        import os
+        import time
+
+        import torch
+
+        from . import exchange as X
+
+        L = _lib.lib()
+        h = self.handle
+        trace = os.environ.get("B200_TRACE") and self.rank == 0
+        t0 = time.perf_counter()
+        slabs = X.get_slabs(self.process_group, self.device) if len(self.key_inds) == 1 else None
+        done = False
+        if slabs is not None:
+            row_bytes = int(L.b200_groupby_exchange_row_bytes(h))
+            cap_rows = (slabs.slab_bytes - X.HDR_BYTES) // (self.n_pes * row_bytes)
+            peers_dev, my_slab, hdl = slabs.next()
+            stream = torch.cuda.ExternalStream(self.stream) if self.stream else torch.cuda.default_stream(self.device)
+            with torch.cuda.stream(stream):
+                _lib.check(L.b200_groupby_exchange_fused_pack(h, ffi.cast("void* const*", peers_dev), cap_rows), "groupby fused exchange (pack)")
+                hdl.barrier(channel=0)
+                _lib.check(L.b200_groupby_exchange_fused_combine(h, ffi.cast("void*", my_slab), cap_rows), "groupby fused exchange (combine)")
+            rc = int(L.b200_groupby_finalize(h))
+            if rc == -1:
+                _lib.check(-1, "groupby finalize")
+            done = rc != -2
+            self.shuffle_bytes = None
+        if not done:
+            self._exchange_nccl()
+            _lib.check(int(L.b200_groupby_finalize(h)), "groupby finalize")
+        self.exchanged = True
+        self.exchange_path = "fused" if done else "nccl"
+        if trace:
+            torch.cuda.synchronize()
+            print(f"[b200 exchange ms] {'fused' if done else 'nccl'} exchange + finalize = {(time.perf_counter() - t0) * 1e3:.3f}", flush=True)
+
+    def _exchange_nccl(self):
+        """The same exchange through NCCL: count all-gather + one all-to-all-v of the packed partial rows, then combine."""
         import os
         import time
 
@@ -147,7 +190,6 @@ class GroupbyState:
                    "groupby shuffle combine")
         L.b200_stream_synchronize(ffi.cast("void*", self.stream))
         mark()
-        self.exchanged = True
         self.shuffle_bytes = n_send * row_bytes
         if trace:
             names = ["prepare", "pack", "counts", "alltoall", "combine"]

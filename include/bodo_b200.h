@@ -90,9 +90,26 @@ int64_t b200_groupby_shuffle_send_bytes(void* state);
 int b200_groupby_shuffle_pack(void* state, void* send_buf);
 int b200_groupby_shuffle_combine(void* state, const void* recv_buf, int64_t n_recv_rows);
 
+/* Fused form of the same exchange (pack + all-to-all in one kernel over NVLink peer memory; what
+ * shuffle_issend/irecv + the combine step do in the reference, streaming/_shuffle.cpp:567-652):
+ * every rank owns a receive slab in memory mapped into all peers (CUDA IPC / symmetric memory, set up once per
+ * process group by the host layer): 256 header bytes + n_pes segments of cap_rows rows of
+ * b200_groupby_exchange_row_bytes(state) bytes.
+ *   1. b200_groupby_exchange_fused_pack: one pass over the local table stores every partial row another rank
+ *      owns straight into that rank's slab (peer_slabs_dev = device array of the n_pes slab addresses) and
+ *      posts the per-source row counts into the peers' headers;
+ *   2. a barrier across the ranks on the same stream (host layer);
+ *   3. b200_groupby_exchange_fused_combine merges the rows received in my_slab.
+ * Nothing here synchronises with the host.  If some rank's share for one destination exceeded cap_rows no
+ * rank combines and b200_groupby_finalize returns -2: run the prepare/pack/combine exchange above and
+ * finalize again (the local tables are intact). */
+int64_t b200_groupby_exchange_row_bytes(void* state);
+int b200_groupby_exchange_fused_pack(void* state, void* const* peer_slabs_dev, int64_t cap_rows);
+int b200_groupby_exchange_fused_combine(void* state, const void* my_slab, int64_t cap_rows);
+
 /* FinalizeBuild (_groupby.cpp:4062-4256): evaluates the output columns (mean_eval etc.). Called
  * implicitly by the first produce call; exposed so the exchange step can be timed separately.
- * Returns the number of output rows (groups owned by this shard). */
+ * Returns the number of output rows (groups owned by this shard), or -2 (see the fused exchange). */
 int64_t b200_groupby_finalize(void* state);
 
 /* groupby_produce_output_batch_py_entry (_groupby.cpp:4772-4783). Fills `out` (caller provides

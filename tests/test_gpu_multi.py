@@ -40,25 +40,39 @@ def _worker(rank, world, port, q):
         lo, hi = rank * chunk, min(n_total, (rank + 1) * chunk)
         df = pd.DataFrame({"k": k[lo:hi], "v": v[lo:hi], "f": vf[lo:hi]})
         t = table_to_device(Table.from_pandas(df), rank)
-        # --- sharded groupby: consume local rows in 3 batches, exchange on the last one ---
+        # --- sharded groupby: consume local rows in 3 batches, exchange on the last one.  Twice: the fused exchange (pack kernel
+        # storing into the owners' slabs over NVLink), then with a slab too small for the partial rows, which must fall back to
+        # the NCCL all-to-all-v without losing or double counting anything ---
         fn = ("sum", "count", "mean", "min", "max")
-        st = init_groupby_state(-1, (0,), fn, (0, 1, 2, 3, 4, 5), (1, 1, 2, 1, 2), parallel=True, expected_groups=64, device=rank,
-                                output_batch_size=1 << 30)
         nloc = hi - lo
         cuts = [0, nloc // 3, 2 * nloc // 3, nloc]
         host = Table.from_pandas(df)
-        for b in range(3):
-            groupby_build_consume_batch(st, table_to_device(host.slice(cuts[b], cuts[b + 1]), rank), b == 2, True)
-        out, last = groupby_produce_output_batch(st, True)
-        got = out.to_pandas()
-        delete_groupby_state(st)
         exp = O.groupby(k, None, list(fn), [v, v, vf, v, vf], n_pes=world, rank=rank)
         e = pd.DataFrame({"k": exp["keys"], **{f"f{j}": c[0] for j, c in enumerate(exp["cols"])}}).sort_values("k").reset_index(drop=True)
-        got.columns = ["k"] + [f"f{j}" for j in range(5)]
-        g = got.sort_values("k").reset_index(drop=True)
-        ok_keys = bool(len(g) == len(e) and (g.k.to_numpy() == e.k.to_numpy()).all())
-        ok_int = ok_keys and all((g[c].to_numpy() == e[c].to_numpy()).all() for c in ("f0", "f1", "f3"))
-        ok_flt = ok_keys and all(np.allclose(g[c].to_numpy(dtype=float), e[c].to_numpy(dtype=float), rtol=1e-5, atol=1e-8) for c in ("f2", "f4"))
+        ok_keys = ok_int = ok_flt = True
+        paths = []
+        from bodo_b200.streaming import exchange as X
+        for slab_bytes in (None, 8192):
+            if slab_bytes is not None:
+                os.environ["B200_XCHG_SLAB_BYTES"] = str(slab_bytes)
+                X._CACHE.clear()
+            st = init_groupby_state(-1, (0,), fn, (0, 1, 2, 3, 4, 5), (1, 1, 2, 1, 2), parallel=True, expected_groups=64, device=rank,
+                                    output_batch_size=1 << 30)
+            for b in range(3):
+                groupby_build_consume_batch(st, table_to_device(host.slice(cuts[b], cuts[b + 1]), rank), b == 2, True)
+            out, last = groupby_produce_output_batch(st, True)
+            got = out.to_pandas()
+            paths.append(st.exchange_path)
+            delete_groupby_state(st)
+            got.columns = ["k"] + [f"f{j}" for j in range(5)]
+            g = got.sort_values("k").reset_index(drop=True)
+            okk = bool(len(g) == len(e) and (g.k.to_numpy() == e.k.to_numpy()).all())
+            ok_keys = ok_keys and okk
+            ok_int = ok_int and okk and all((g[c].to_numpy() == e[c].to_numpy()).all() for c in ("f0", "f1", "f3"))
+            ok_flt = ok_flt and okk and all(np.allclose(g[c].to_numpy(dtype=float), e[c].to_numpy(dtype=float), rtol=1e-5, atol=1e-8) for c in ("f2", "f4"))
+        os.environ.pop("B200_XCHG_SLAB_BYTES", None)
+        X._CACHE.clear()
+        ok_keys = ok_keys and paths[1] == "nccl"  # (paths[0] is "fused" wherever symmetric memory is available)
         # --- shuffle_table over NCCL: rows land on hash_to_rank(key), nothing lost ---
         sh = shuffle_table(t, 1, True)
         sdf = sh.to_pandas()
@@ -67,7 +81,7 @@ def _worker(rank, world, port, q):
         tot = torch.tensor([len(sdf), int(sdf["v"].sum()), nloc, int(df["v"].sum())], dtype=torch.int64, device=f"cuda:{rank}")
         dist.all_reduce(tot)
         ok_cons = tot[0].item() == tot[2].item() and tot[1].item() == tot[3].item()
-        q.put((rank, ok_keys, ok_int, ok_flt, ok_owner, ok_cons))
+        q.put((rank, ok_keys, ok_int, ok_flt, ok_owner, ok_cons, paths))
     except Exception:
         import traceback
         q.put((rank, traceback.format_exc()))
@@ -90,7 +104,8 @@ def test_sharded_groupby_and_shuffle_nccl(gpu_lib):
     for p in procs:
         p.join(timeout=60)
     for r in sorted(res, key=lambda x: x[0]):
-        assert len(r) == 6 and all(r[1:]), r
+        assert len(r) == 7 and all(r[1:6]), r
+    print("exchange paths per run:", sorted(res, key=lambda x: x[0])[0][6])
 
 
 def _join_worker(rank, world, port, q):
