@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 
 #include <stdexcept>
 #include <string>
@@ -84,6 +85,45 @@ __host__ __device__ __forceinline__ uint64_t xxh3_64_short(uint64_t raw, int len
     return h ^ (h >> 28);
 }
 
+// hash_combine_boost (reference: bodo/libs/_array_hash.cpp:41-56): one 32-bit murmur round folding a further key column's
+// hash into the running row hash.
+__host__ __device__ __forceinline__ uint32_t hash_combine_boost(uint32_t h1, uint32_t k1) {
+    k1 *= 0xcc9e2d51u;
+    k1 = (k1 << 15) | (k1 >> 17);
+    k1 *= 0x1b873593u;
+    h1 ^= k1;
+    h1 = (h1 << 13) | (h1 >> 19);
+    return h1 * 5u + 0xe6546b64u;
+}
+// _Py_HashDouble (CPython Python/pyhash.c, what the reference feeds float keys through before hashing the resulting
+// Py_hash_t, bodo/libs/_array_hash.cpp:119-170): reduction of the double modulo the Mersenne prime 2^61 - 1; NaN -> 0 (the
+// reference passes a NULL identity), +-inf -> +-314159.  Restated from the published algorithm; pinned against the oracle
+// (which is pinned against the interpreter's own hash(float)) in tests/test_gpu_shuffle.py.
+__host__ __device__ inline int64_t py_hash_double(double v) {
+    const int BITS = 61;
+    const uint64_t MOD = (1ULL << 61) - 1;
+    if (isnan(v)) return 0;
+    if (isinf(v)) return v > 0 ? 314159 : -314159;
+    int e;
+    double m = frexp(v, &e);
+    int sign = 1;
+    if (m < 0) { sign = -1; m = -m; }
+    uint64_t x = 0;
+    while (m != 0.0) {
+        x = ((x << 28) & MOD) | (x >> (BITS - 28));
+        m *= 268435456.0;  // 2^28
+        e -= 28;
+        uint64_t y = (uint64_t)m;
+        m -= (double)y;
+        x += y;
+        if (x >= MOD) x -= MOD;
+    }
+    e = e >= 0 ? e % BITS : BITS - 1 - ((-1 - e) % BITS);
+    x = ((x << e) & MOD) | (x >> (BITS - e));
+    int64_t r = (int64_t)x * sign;
+    return r == -1 ? -2 : r;
+}
+
 // hash_to_rank (reference: bodo/libs/_shuffle.h:5-7): (uint32) hash % n_pes.
 __host__ __device__ __forceinline__ int hash_to_rank_u32(uint32_t h, int n_pes) { return (int)(h % (uint32_t)n_pes); }
 
@@ -109,6 +149,29 @@ __device__ __forceinline__ double load_as_f64(const void* __restrict__ p, int ct
         case CT_FLOAT32: return (double)((const float*)p)[i];
         default: return (double)load_int_as_i64(p, ct, i);
     }
+}
+
+// hash_keys (reference: bodo/libs/_array_hash.cpp:1599-1621) of one row over 1..MAX_HASH_KEYS key columns: the first column is
+// hashed (hash_array_inner: sizeof(T) raw bytes of an integer / date column through XXH3, a float column through
+// _Py_HashDouble first; NA -> hash_na_val = hash of int64 1), every further column's hash is folded in with
+// hash_combine_boost.  Low 32 bits of the XXH3 value, as hash_inner_32 returns them.
+constexpr int MAX_HASH_KEYS = 4;
+struct KeySet {
+    int n_keys;
+    const void* data[MAX_HASH_KEYS];
+    const uint8_t* valid[MAX_HASH_KEYS];
+    int ctype[MAX_HASH_KEYS];
+};
+__device__ __forceinline__ uint32_t hash_key_column(const void* data, int ct, const uint8_t* valid, int64_t i, uint32_t seed) {
+    if (!bit_valid(valid, i)) return (uint32_t)xxh3_64_short(1ull, 8, seed);
+    if (ct == CT_FLOAT64 || ct == CT_FLOAT32) return (uint32_t)xxh3_64_short((uint64_t)py_hash_double(load_as_f64(data, ct, i)), 8, seed);
+    if (ctype_size(ct) == 8) return (uint32_t)xxh3_64_short((uint64_t)load_int_as_i64(data, ct, i), 8, seed);
+    return (uint32_t)xxh3_64_short((uint64_t)(uint32_t)load_int_as_i64(data, ct, i), 4, seed);  // 4-byte keys hash their 4 raw bytes
+}
+__device__ __forceinline__ uint32_t hash_keys_row(const KeySet& k, int64_t i, uint32_t seed) {
+    uint32_t h = hash_key_column(k.data[0], k.ctype[0], k.valid[0], i, seed);
+    for (int j = 1; j < k.n_keys; j++) h = hash_combine_boost(h, hash_key_column(k.data[j], k.ctype[j], k.valid[j], i, seed));
+    return h;
 }
 
 // order-preserving double <-> uint64 encoding (so float min/max are native 64-bit integer atomics)

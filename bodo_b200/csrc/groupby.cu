@@ -425,23 +425,10 @@ struct CombineArgs {
     void* a1[MAX_OPS];
 };
 // combine step (get_combine_func, groupby/_groupby_update.cpp:41-57): count/size/mean -> sum, min -> min, max -> max
-__device__ __forceinline__ void combine_one_row(const CombineArgs& a, int64_t row) {
+// merges the accumulator words r[0 ...] of one partial row into `slot`
+__device__ __forceinline__ void combine_apply(const CombineArgs& a, uint64_t slot, const unsigned long long* r) {
     {
-        const unsigned long long* r = a.in + row * a.row_words;
-        long long key = (long long)r[0];
-        bool kvalid = r[1] & 1;
-        uint64_t slot;
-        if (!kvalid) { slot = a.cap; a.counters[3] = 1; }
-        else if (key == EMPTY_KEY) { slot = a.cap + 1; a.counters[4] = 1; }
-        else {
-            slot = find_or_insert(a.tkeys, a.cap, key, a.counters, a.group_limit);
-            if (slot == ~0ull) {
-                unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
-                a.fail_list[f] = (uint32_t)row;
-                return;
-            }
-        }
-        int w = 2;
+        int w = 0;
         for (int j = 0; j < a.n_ops; j++) {
             unsigned long long v0 = r[w++];
             unsigned long long v1 = a.a1[j] ? r[w++] : 0;
@@ -460,6 +447,23 @@ __device__ __forceinline__ void combine_one_row(const CombineArgs& a, int64_t ro
             if (a.a1[j] && a.kinds[j] != K_MEAN) atomicAdd((unsigned long long*)a.a1[j] + slot, v1);
         }
     }
+}
+__device__ __forceinline__ void combine_one_row(const CombineArgs& a, int64_t row) {
+    const unsigned long long* r = a.in + row * a.row_words;
+    long long key = (long long)r[0];
+    bool kvalid = r[1] & 1;
+    uint64_t slot;
+    if (!kvalid) { slot = a.cap; a.counters[3] = 1; }
+    else if (key == EMPTY_KEY) { slot = a.cap + 1; a.counters[4] = 1; }
+    else {
+        slot = find_or_insert(a.tkeys, a.cap, key, a.counters, a.group_limit);
+        if (slot == ~0ull) {
+            unsigned long long f = atomicAdd((unsigned long long*)&a.counters[1], 1ull);
+            a.fail_list[f] = (uint32_t)row;
+            return;
+        }
+    }
+    combine_apply(a, slot, r + 2);
 }
 __global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -654,10 +658,36 @@ __global__ void rehash_mk_kernel(const __grid_constant__ RehashMkArgs a) {
         for (int j = 0; j < a.n_acc; j++) a.new_acc[j][ns] = a.old_acc[j][s];
     }
 }
-__global__ void compact_mk_kernel(const unsigned long long* __restrict__ tags, uint64_t cap, long long* cursor, uint64_t* slot_of_out) {
+// Ownership of a multi-column key: hash_keys of the tuple exactly as the reference computes it on the original columns
+// (sizeof(T) raw bytes per integer column, NA -> hash_na_val, hash_combine_boost for the further columns), from the
+// widened int64 values the table stores.
+struct MkOwner {
+    int nk, n_pes, rank;
+    const long long* mk[MAX_KEYS];
+    const unsigned char* mkmask;
+    int key_ctype[MAX_KEYS];
+};
+__device__ __forceinline__ uint32_t mk_ref_hash(const long long* keys, unsigned int mask, int nk, const int* ctypes) {
+    const uint32_t na_hash = (uint32_t)xxh3_64_short(1ull, 8, SEED_HASH_PARTITION);
+    uint32_t h = 0;
+    for (int j = 0; j < nk; j++) {
+        const uint32_t hj = !((mask >> j) & 1u) ? na_hash
+                           : ctype_size(ctypes[j]) == 8 ? (uint32_t)xxh3_64_short((uint64_t)keys[j], 8, SEED_HASH_PARTITION)
+                                                        : (uint32_t)xxh3_64_short((uint64_t)(uint32_t)keys[j], 4, SEED_HASH_PARTITION);
+        h = j == 0 ? hj : hash_combine_boost(h, hj);
+    }
+    return h;
+}
+__global__ void compact_mk_kernel(const unsigned long long* __restrict__ tags, uint64_t cap, long long* cursor, uint64_t* slot_of_out,
+                                  const __grid_constant__ MkOwner ow) {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t s0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s0 < ((cap + 31) & ~31ull); s0 += stride) {
         bool occ = s0 < cap && (tags[s0] >> 63);
+        if (occ && ow.n_pes > 1) {  // only the groups this rank owns (see compact_slots_kernel)
+            long long keys[MAX_KEYS];
+            for (int j = 0; j < ow.nk; j++) keys[j] = ow.mk[j][s0];
+            occ = hash_to_rank_u32(mk_ref_hash(keys, ow.mkmask[s0], ow.nk, ow.key_ctype), ow.n_pes) == ow.rank;
+        }
         unsigned m = __ballot_sync(0xffffffffu, occ);
         int lane = threadIdx.x & 31;
         long long base = 0;
@@ -666,6 +696,79 @@ __global__ void compact_mk_kernel(const unsigned long long* __restrict__ tags, u
         if (occ) slot_of_out[base + __popc(m & ((1u << lane) - 1))] = s0;
     }
 }
+// ---- fused exchange for multi-column keys: wire row = [key 0 .. key nk-1][NA mask][accumulators] ----
+struct XchgPackMkArgs {
+    MkOwner ow;
+    const unsigned long long* tags;
+    uint64_t cap;
+    int n_acc;
+    const unsigned long long* acc[2 * MAX_OPS];
+    int row_words;
+    unsigned long long* cursors;
+    void* const* peer_slabs;
+    long long cap_rows;
+};
+__global__ void xchg_pack_remote_mk_kernel(const __grid_constant__ XchgPackMkArgs a) {
+    const int lane = threadIdx.x & 31;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < ((a.cap + 31) & ~31ull); s += stride) {
+        const bool occ = s < a.cap && (a.tags[s] >> 63);
+        long long keys[MAX_KEYS];
+        unsigned int mask = 0;
+        int d = -1;
+        if (occ) {
+            for (int j = 0; j < a.ow.nk; j++) keys[j] = a.ow.mk[j][s];
+            mask = a.ow.mkmask[s];
+            d = hash_to_rank_u32(mk_ref_hash(keys, mask, a.ow.nk, a.ow.key_ctype), a.ow.n_pes);
+            if (d == a.ow.rank) d = -1;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        const int rank_in_peers = __popc(peers & ((1u << lane) - 1));
+        unsigned long long base = 0;
+        if (d >= 0 && lane == leader) base = atomicAdd(&a.cursors[d], (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (d >= 0) {
+            const unsigned long long pos = base + rank_in_peers;
+            if (pos < (unsigned long long)a.cap_rows) {
+                unsigned long long* o = (unsigned long long*)((char*)a.peer_slabs[d] + XCHG_HDR_BYTES) + ((size_t)a.ow.rank * a.cap_rows + pos) * a.row_words;
+                for (int j = 0; j < a.ow.nk; j++) o[j] = (unsigned long long)keys[j];
+                o[a.ow.nk] = mask;
+                for (int j = 0; j < a.n_acc; j++) o[a.ow.nk + 1 + j] = a.acc[j][s];
+            }
+        }
+    }
+}
+// combine of received multi-key rows: hdr != nullptr: the slab's n_pes segments; else the rows listed in c.index_list
+__global__ void xchg_combine_mk_kernel(const __grid_constant__ MkArgs m, const __grid_constant__ CombineArgs c, const unsigned long long* hdr,
+                                       int n_pes, long long cap_rows) {
+    auto one = [&](int64_t row) {
+        const unsigned long long* r = c.in + row * c.row_words;
+        long long keys[MAX_KEYS];
+        for (int j = 0; j < m.nk; j++) keys[j] = (long long)r[j];
+        const unsigned int mask = (unsigned int)r[m.nk];
+        const uint64_t slot = find_or_insert_mk(m, keys, mask, mk_tag(keys, mask, m.nk));
+        if (slot == ~0ull) {
+            unsigned long long f = atomicAdd((unsigned long long*)&c.counters[1], 1ull);
+            c.fail_list[f] = (uint32_t)row;
+            return;
+        }
+        combine_apply(c, slot, r + m.nk + 1);
+    };
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (hdr == nullptr) {
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < c.n_rows; i += stride) one((int64_t)c.index_list[i]);
+        return;
+    }
+    bool over = false;
+    for (int s = 0; s < n_pes; s++) over |= (hdr[s] & XCHG_OVERFLOW) != 0;
+    if (over) { if (blockIdx.x == 0 && threadIdx.x == 0) c.counters[7] = 1; return; }
+    for (int s = 0; s < n_pes; s++) {
+        const int64_t n = (int64_t)(hdr[s] & ~XCHG_OVERFLOW);
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) one((int64_t)s * cap_rows + i);
+    }
+}
+
 struct EvalMkKeysArgs {
     int nk;
     const long long* mk[MAX_KEYS];
@@ -1545,7 +1648,6 @@ class GroupbyState {
           n_pes(n_pes_), rank(rank_), output_batch_size(out_bs) {
         B200_REQUIRE(n_keys >= 1 && n_keys <= (uint64_t)MAX_KEYS, "b200 groupby: between 1 and 4 key columns are supported");
         nk = (int)n_keys;
-        B200_REQUIRE(!(nk > 1 && parallel_ && n_pes_ > 1), "b200 groupby: multi-column keys are not supported on the sharded (parallel) path yet");
         B200_REQUIRE(n_arrs >= 1, "b200 groupby: empty build schema");
         B200_REQUIRE(n_funcs_ <= MAX_OPS, "b200 groupby: too many aggregate functions");
         c_types.assign(ct, ct + n_arrs);
@@ -2215,7 +2317,8 @@ class GroupbyState {
         d_slot_of_out.ensure((size_t)max_out * 8);
         B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 16, 0, 8, stream));
         if (nk > 1)
-            compact_mk_kernel<<<grid_for((int64_t)cap), 256, 0, stream>>>(d_tags.as<unsigned long long>(), cap, d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>());
+            compact_mk_kernel<<<grid_for((int64_t)cap), 256, 0, stream>>>(d_tags.as<unsigned long long>(), cap, d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>(),
+                                                                           mk_owner(owned_only));
         else
             compact_slots_kernel<<<grid_for((int64_t)cap + 2), 256, 0, stream>>>(d_keys.as<long long>(), cap, d_counters.as<long long>(),
                                                                                       d_counters.as<long long>() + 2, d_slot_of_out.as<uint64_t>(),
@@ -2285,6 +2388,8 @@ class GroupbyState {
                 B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8, 0, 8, stream));
                 CombineArgs c = combine_args((const unsigned long long*)((const char*)xchg_slab + XCHG_HDR_BYTES), nf, /*group_limit=*/-1);
                 c.index_list = replay_list.as<uint32_t>();
+                if (nk > 1) { c.row_words = nk + 1 + acc_count(); MkArgs m = mk_table_args(); m.group_limit = -1; xchg_combine_mk_kernel<<<grid_for(nf), 256, 0, stream>>>(m, c, nullptr, n_pes, 0); }
+                else
                 combine_partials_kernel<<<grid_for(nf), 256, 0, stream>>>(c);
                 launches++;
                 B200_CUDA(cudaGetLastError());
@@ -2298,6 +2403,19 @@ class GroupbyState {
         return n_out;
     }
 
+    MkOwner mk_owner(bool owned_only) {
+        MkOwner o{};
+        o.nk = nk; o.n_pes = owned_only ? n_pes : 1; o.rank = rank; o.mkmask = d_mkmask.as<unsigned char>();
+        for (int j = 0; j < nk; j++) { o.mk[j] = d_mk[j].as<long long>(); o.key_ctype[j] = c_types[j]; }
+        return o;
+    }
+    MkArgs mk_table_args() {
+        MkArgs a{};
+        a.nk = nk; a.tags = d_tags.as<unsigned long long>(); a.mkmask = d_mkmask.as<unsigned char>(); a.cap = cap;
+        for (int j = 0; j < nk; j++) a.mk[j] = d_mk[j].as<long long>();
+        a.counters = d_counters.as<long long>(); a.group_limit = (long long)(cap / 2); a.fail_list = d_fail.as<uint32_t>();
+        return a;
+    }
     // ---- fused exchange (see xchg_pack_remote_kernel) ----
     bool xchg_fused = false;
     const void* xchg_slab = nullptr;
@@ -2310,13 +2428,27 @@ class GroupbyState {
         for (int j = 0; j < n_funcs; j++) { c.kinds[j] = funcs[j].kind; c.a0[j] = d_a0[j].p; c.a1[j] = funcs[j].has_a1 ? d_a1[j].p : nullptr; }
         return c;
     }
-    int64_t xchg_row_bytes() const { return (int64_t)(2 + acc_count()) * 8; }
+    int64_t xchg_row_bytes() const { return (int64_t)((nk == 1 ? 2 : nk + 1) + acc_count()) * 8; }
     void exchange_fused_pack(void* const* peer_slabs_dev, int64_t cap_rows) {
         B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
-        B200_REQUIRE(nk == 1, "b200 groupby: the fused exchange handles single-column keys");
         build_done = true;
         d_xchg_cursors.ensure((size_t)std::max(n_pes, 32) * 8);
         B200_CUDA(cudaMemsetAsync(d_xchg_cursors.p, 0, (size_t)std::max(n_pes, 32) * 8, stream));
+        if (nk > 1) {
+            XchgPackMkArgs p{};
+            p.ow = mk_owner(true); p.tags = d_tags.as<unsigned long long>(); p.cap = cap;
+            int n = 0;
+            for (int j = 0; j < n_funcs; j++) {
+                p.acc[n++] = d_a0[j].as<unsigned long long>();
+                if (funcs[j].has_a1) p.acc[n++] = d_a1[j].as<unsigned long long>();
+            }
+            p.n_acc = n; p.row_words = nk + 1 + n; p.cursors = d_xchg_cursors.as<unsigned long long>(); p.peer_slabs = peer_slabs_dev; p.cap_rows = cap_rows;
+            xchg_pack_remote_mk_kernel<<<grid_for((int64_t)cap), 256, 0, stream>>>(p);
+            xchg_post_counts_kernel<<<1, 32, 0, stream>>>(d_xchg_cursors.as<unsigned long long>(), peer_slabs_dev, n_pes, rank, cap_rows);
+            launches += 2;
+            B200_CUDA(cudaGetLastError());
+            return;
+        }
         XchgPackArgs p{};
         p.tkeys = d_keys.as<long long>(); p.cap = cap; p.counters = d_counters.as<long long>(); p.n_pes = n_pes; p.rank = rank;
         int n = 0;
@@ -2334,6 +2466,8 @@ class GroupbyState {
         B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         d_fail.ensure(device, (size_t)n_pes * (size_t)cap_rows * 4);
         CombineArgs c = combine_args((const unsigned long long*)((const char*)my_slab + XCHG_HDR_BYTES), 0, (long long)(cap / 2));
+        if (nk > 1) { c.row_words = nk + 1 + acc_count(); xchg_combine_mk_kernel<<<grid_for(std::min<int64_t>(cap_rows, 1 << 22)), 256, 0, stream>>>(mk_table_args(), c, (const unsigned long long*)my_slab, n_pes, cap_rows); }
+        else
         xchg_combine_slab_kernel<<<grid_for(std::min<int64_t>(cap_rows, 1 << 22)), 256, 0, stream>>>(c, (const unsigned long long*)my_slab, n_pes, cap_rows);
         launches++;
         B200_CUDA(cudaGetLastError());
@@ -2347,6 +2481,7 @@ class GroupbyState {
     // ---- exchange ----
     int64_t shuffle_prepare(int64_t* send_counts) {
         B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
+        B200_REQUIRE(nk == 1, "b200 groupby: multi-column keys on the sharded path use the fused exchange (symmetric memory); the NCCL form handles single-column keys");
         build_done = true;
         compact(/*owned_only=*/false);
         read_counters();

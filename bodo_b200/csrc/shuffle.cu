@@ -25,22 +25,17 @@ constexpr int PART_THREADS = 256;
 constexpr int MAX_PES = 256;
 constexpr int MAX_SHUFFLE_COLS = 32;
 
-__device__ __forceinline__ uint32_t row_hash32(const void* key_data, int key_ctype, const uint8_t* key_valid, int64_t i) {
-    if (!bit_valid(key_valid, i)) return (uint32_t)xxh3_64_short(1ull, 8, SEED_HASH_PARTITION);  // hash_na_val
-    if (ctype_size(key_ctype) == 8) return (uint32_t)xxh3_64_short((uint64_t)load_int_as_i64(key_data, key_ctype, i), 8, SEED_HASH_PARTITION);
-    // 4-byte keys hash their 4 raw bytes (hash_inner_32<T> uses sizeof(T))
-    return (uint32_t)xxh3_64_short((uint64_t)(uint32_t)load_int_as_i64(key_data, key_ctype, i), 4, SEED_HASH_PARTITION);
-}
-
-__global__ void hash_to_rank_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid, int64_t n, int n_pes,
-                                    int32_t* dest) {
+__global__ void hash_to_rank_kernel(const __grid_constant__ KeySet k, int64_t n, int n_pes, int32_t* dest, uint32_t* hash_out) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride)
-        dest[i] = hash_to_rank_u32(row_hash32(key_data, key_ctype, key_valid, i), n_pes);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t h = hash_keys_row(k, i, SEED_HASH_PARTITION);
+        if (dest) dest[i] = hash_to_rank_u32(h, n_pes);
+        if (hash_out) hash_out[i] = h;
+    }
 }
 
 // K1: tile = contiguous rows [cta * tile_rows, ...). dest8 holds the destination of every row.
-__global__ void __launch_bounds__(PART_THREADS) dest_hist_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid,
+__global__ void __launch_bounds__(PART_THREADS) dest_hist_kernel(const __grid_constant__ KeySet k,
                                                                  int64_t n, int64_t tile_rows, int n_pes, uint8_t* dest8,
                                                                  unsigned int* hist /* [gridDim.x][n_pes] */) {
     __shared__ unsigned int sh[MAX_PES];
@@ -49,7 +44,7 @@ __global__ void __launch_bounds__(PART_THREADS) dest_hist_kernel(const void* key
     int64_t r0 = (int64_t)blockIdx.x * tile_rows;
     int64_t r1 = r0 + tile_rows < n ? r0 + tile_rows : n;
     for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
-        int d = hash_to_rank_u32(row_hash32(key_data, key_ctype, key_valid, i), n_pes);
+        int d = hash_to_rank_u32(hash_keys_row(k, i, SEED_HASH_PARTITION), n_pes);
         dest8[i] = (uint8_t)d;
         atomicAdd(&sh[d], 1u);
     }
@@ -197,18 +192,28 @@ static int table_device(const b200_table* t) {
     B200_REQUIRE(t->device >= 0, "b200 shuffle: the table must be device resident");
     return t->device;
 }
+// the first n_keys columns as a KeySet (4- / 8-byte integer, date and float columns)
+static KeySet make_keyset(const b200_table* t, int n_keys) {
+    KeySet k{};
+    k.n_keys = n_keys;
+    for (int j = 0; j < n_keys; j++) {
+        const b200_column& c = t->cols[j];
+        B200_REQUIRE(ctype_size(c.c_type) == 4 || ctype_size(c.c_type) == 8, "b200 shuffle: key columns must be 4- or 8-byte integer, date or float columns");
+        k.data[j] = c.data; k.valid[j] = c.validity; k.ctype[j] = c.c_type;
+    }
+    return k;
+}
 
 void shuffle_partition(const b200_table* in, int64_t n_keys, int n_pes, b200_table* out, int64_t* send_counts,
                        long long* perm_out_dev, cudaStream_t st) {
-    B200_REQUIRE(n_keys == 1, "b200 shuffle: exactly one key column is supported");
+    B200_REQUIRE(n_keys >= 1 && n_keys <= MAX_HASH_KEYS && n_keys <= in->n_cols, "b200 shuffle: between 1 and 4 key columns are supported");
     B200_REQUIRE(n_pes >= 1 && n_pes <= MAX_PES, "b200 shuffle: n_pes must be in [1, 256]");
     B200_REQUIRE(in->n_cols >= 1 && in->n_cols <= MAX_SHUFFLE_COLS, "b200 shuffle: between 1 and 32 columns are supported");
     B200_REQUIRE(out->n_cols == in->n_cols, "b200 shuffle: out table must have the same number of columns");
     int dev = table_device(in);
     B200_CUDA(cudaSetDevice(dev));
     int64_t n = in->n_rows;
-    int kct = in->cols[0].c_type;
-    B200_REQUIRE((ctype_size(kct) == 4 || ctype_size(kct) == 8) && !ctype_is_float(kct), "b200 shuffle: key must be a 4- or 8-byte integer/date column");
+    KeySet ks = make_keyset(in, (int)n_keys);
     for (int d = 0; d < n_pes; d++) send_counts[d] = 0;
     out->n_rows = n;
     if (n == 0) return;
@@ -217,8 +222,7 @@ void shuffle_partition(const b200_table* in, int64_t n_keys, int n_pes, b200_tab
     int64_t tile_rows = ((n + n_ctas - 1) / n_ctas + PART_THREADS - 1) / PART_THREADS * PART_THREADS;
     n_ctas = (int)((n + tile_rows - 1) / tile_rows);
     StreamBuf dest8((size_t)n, st), hist((size_t)n_ctas * n_pes * 4, st), offsets((size_t)n_ctas * n_pes * 8, st), totals((size_t)n_pes * 8, st);
-    dest_hist_kernel<<<n_ctas, PART_THREADS, 0, st>>>(in->cols[0].data, kct, in->cols[0].validity, n, tile_rows, n_pes,
-                                                      dest8.as<uint8_t>(), hist.as<unsigned int>());
+    dest_hist_kernel<<<n_ctas, PART_THREADS, 0, st>>>(ks, n, tile_rows, n_pes, dest8.as<uint8_t>(), hist.as<unsigned int>());
     B200_CUDA(cudaGetLastError());
     scan_hist_kernel<<<1, 256, 0, st>>>(hist.as<unsigned int>(), n_ctas, n_pes, offsets.as<long long>(), totals.as<long long>());
     B200_CUDA(cudaGetLastError());
@@ -259,14 +263,18 @@ void shuffle_partition(const b200_table* in, int64_t n_keys, int n_pes, b200_tab
 extern "C" {
 
 int b200_hash_to_rank(const b200_table* in_table, int32_t n_pes, int32_t* dest_out, void* stream) {
+    return b200_hash_keys_table(in_table, in_table ? 1 : 0, n_pes, dest_out, nullptr, stream);
+}
+
+int b200_hash_keys_table(const b200_table* in_table, int64_t n_keys, int32_t n_pes, int32_t* dest_out, uint32_t* hash_out, void* stream) {
     try {
-        B200_REQUIRE(in_table && in_table->n_cols >= 1 && n_pes >= 1, "b200_hash_to_rank: bad arguments");
+        B200_REQUIRE(in_table && n_keys >= 1 && n_keys <= b200::MAX_HASH_KEYS && in_table->n_cols >= n_keys && n_pes >= 1 && (dest_out || hash_out),
+                     "b200_hash_keys_table: bad arguments");
         int dev = b200::table_device(in_table);
         B200_CUDA(cudaSetDevice(dev));
         if (in_table->n_rows == 0) return 0;
-        const b200_column& k = in_table->cols[0];
-        B200_REQUIRE((b200::ctype_size(k.c_type) == 4 || b200::ctype_size(k.c_type) == 8) && !b200::ctype_is_float(k.c_type), "b200_hash_to_rank: key must be a 4- or 8-byte integer/date column");
-        b200::hash_to_rank_kernel<<<b200::num_sms(dev) * 8, 256, 0, (cudaStream_t)stream>>>(k.data, k.c_type, k.validity, in_table->n_rows, n_pes, dest_out);
+        b200::KeySet ks = b200::make_keyset(in_table, (int)n_keys);
+        b200::hash_to_rank_kernel<<<b200::num_sms(dev) * 8, 256, 0, (cudaStream_t)stream>>>(ks, in_table->n_rows, n_pes, dest_out, hash_out);
         B200_CUDA(cudaGetLastError());
         return 0;
     } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }

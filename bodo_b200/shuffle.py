@@ -55,6 +55,23 @@ def partition_device(table: Table, n_keys: int, n_pes: int, stream: int = 0, wan
     return out, [int(counts[i]) for i in range(n_pes)]
 
 
+def hash_keys_table(table: Table, n_keys: int = 1, n_pes: int = 1, stream: int = 0):
+    """hash_keys_table(table, n_keys, SEED_HASH_PARTITION) on the device (b200_hash_keys_table): returns (row hashes as an
+    int64-viewable uint32 tensor, destination ranks) for a device-resident table whose first n_keys columns are the keys."""
+    import torch
+
+    L = _lib.lib()
+    _lib.require_gpu()
+    dev = torch.device("cuda", table.device)
+    n = table.n_rows
+    hashes = torch.empty(n, dtype=torch.int32, device=dev)  # uint32 bit patterns
+    dest = torch.empty(n, dtype=torch.int32, device=dev)
+    ct = CTable(table)
+    _lib.check(L.b200_hash_keys_table(ct.ptr, n_keys, n_pes, ffi.cast("int32_t*", dest.data_ptr()), ffi.cast("uint32_t*", hashes.data_ptr()),
+                                      ffi.cast("void*", stream)), "hash_keys_table")
+    return hashes, dest
+
+
 def _np_dtype(c: Column):
     from .table import np_dtype_of
 

@@ -119,7 +119,7 @@ class GroupbyState:
         h = self.handle
         trace = os.environ.get("B200_TRACE") and self.rank == 0
         t0 = time.perf_counter()
-        slabs = X.get_slabs(self.process_group, self.device) if len(self.key_inds) == 1 else None
+        slabs = X.get_slabs(self.process_group, self.device)
         done = False
         if slabs is not None:
             row_bytes = int(L.b200_groupby_exchange_row_bytes(h))

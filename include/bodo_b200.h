@@ -168,6 +168,12 @@ int64_t b200_join_get_metric(void* state, int32_t which);
  * _shuffle.h:5-7): dest[i] = (uint32)XXH3_64bits_withSeed(&key[i], 8, 0xb0d01289) % n_pes. Writes
  * per-row destinations (device int32) — exposed for placement-parity tests. */
 int b200_hash_to_rank(const b200_table* in_table, int32_t n_pes, int32_t* dest_out, void* stream);
+/* hash_keys_table(table, n_keys, SEED_HASH_PARTITION) (bodo/libs/_array_hash.cpp:1599-1621) over the first n_keys (1..4)
+ * columns: integer / date columns hash their sizeof(T) raw bytes, float columns go through _Py_HashDouble first
+ * (:119-170), NA -> hash_na_val, further columns are folded in with hash_combine_boost (:41-56).  Writes the 32-bit row
+ * hashes (hash_out, device uint32, may be NULL) and / or hash % n_pes (dest_out, device int32, may be NULL). */
+int b200_hash_keys_table(const b200_table* in_table, int64_t n_keys, int32_t n_pes, int32_t* dest_out,
+                         uint32_t* hash_out, void* stream);
 
 /* mpi_comm_info::set_send_count + fill_send_array (bodo/libs/_shuffle.cpp:94-163,345-368,477+) as one
  * radix-partition pass: histogram of destinations, exclusive scan, stable scatter of every column
