@@ -17,7 +17,8 @@ enum CType : int { CT_INT8 = 0, CT_UINT8 = 1, CT_INT32 = 2, CT_UINT32 = 3, CT_IN
                    CT_TIMEDELTA = 16 };
 enum ArrType : int { ARR_NUMPY = 0, ARR_NULLABLE = 2 };
 // Bodo_FTypes (reference: bodo/libs/groupby/_groupby_ftypes.h:17-110)
-enum FType : int { FT_SIZE = 4, FT_SUM = 6, FT_COUNT = 7, FT_MEAN = 14, FT_MIN = 15, FT_MAX = 16 };
+enum FType : int { FT_SIZE = 4, FT_SUM = 6, FT_COUNT = 7, FT_NUNIQUE = 8, FT_MEAN = 14, FT_MIN = 15, FT_MAX = 16, FT_FIRST = 18, FT_LAST = 19,
+                   FT_VAR_POP = 22, FT_STD_POP = 23, FT_VAR = 24, FT_STD = 25, FT_SKEW = 27 };
 
 // hash seeds (reference: bodo/libs/_array_hash.h:8-14)
 constexpr uint32_t SEED_HASH_PARTITION = 0xb0d01289u;

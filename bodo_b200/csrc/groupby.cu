@@ -24,10 +24,13 @@
 namespace b200 {
 
 constexpr long long EMPTY_KEY = (long long)0x8000000000000000ULL;  // INT64_MIN marks a free slot
-constexpr int MAX_OPS = 12;
+constexpr int MAX_OPS = 16;
 constexpr int64_t CHUNK_ROWS = 1ll << 27;  // rows per kernel launch (bounds the fail list at 512 MiB)
 
-enum OpKind : int { K_SUM_I64 = 0, K_SUM_F64, K_COUNT, K_SIZE, K_MEAN, K_MIN_I64, K_MAX_I64, K_MIN_F64, K_MAX_F64 };
+enum OpKind : int { K_SUM_I64 = 0, K_SUM_F64, K_COUNT, K_SIZE, K_MEAN, K_MIN_I64, K_MAX_I64, K_MIN_F64, K_MAX_F64,
+                    K_SUMSQ_F64, K_SUMCUBE_F64,  // hidden accumulators: sum of squares / cubes (as double) of the non-NA values
+                    // evaluation-only kinds of composite functions (accumulators: a K_MEAN pair + K_SUMSQ (+ K_SUMCUBE))
+                    E_VAR, E_STD, E_VAR_POP, E_STD_POP, E_SKEW };
 
 struct OpDesc {
     int kind;
@@ -116,6 +119,11 @@ __device__ __forceinline__ void apply_ops(const A& a, uint64_t slot, int64_t row
                     atomicAdd((double*)op.a0 + slot, v);
                     atomicAdd((unsigned long long*)op.a1 + slot, 1ull);
                 }
+                break;
+            }
+            case K_SUMSQ_F64: case K_SUMCUBE_F64: {  // skew_agg's m2 / m3 (:723-745); var / std use m2 with the K_MEAN pair
+                double v = load_as_f64(op.in_data, op.in_ctype, row);
+                if (!isnan(v)) atomicAdd((double*)op.a0 + slot, op.kind == K_SUMSQ_F64 ? v * v : v * v * v);
                 break;
             }
             case K_MIN_I64:
@@ -279,6 +287,8 @@ struct OutDesc {
     int out_ctype;  // CType of the output column
     const void* a0;
     const void* a1;
+    const void* b0;  // composite functions: sum of squares
+    const void* c0;  //                      sum of cubes
     void* out_data;
     uint32_t* out_valid;  // validity bitmap as 32-bit words, or nullptr when the column has no nulls
 };
@@ -341,6 +351,36 @@ __global__ void eval_output_kernel(const __grid_constant__ EvalArgs a) {
                         unsigned long long c = ((const unsigned long long*)op.a1)[s];
                         valid = c > 0;
                         store_f_typed(op.out_data, op.out_ctype, p, valid ? ((const double*)op.a0)[s] / (double)c : __longlong_as_double(0x7ff8000000000000ll));
+                        break;
+                    }
+                    case E_VAR: case E_STD: case E_VAR_POP: case E_STD_POP: {
+                        // var_eval / std_eval (groupby/_groupby_eval.h:71-95).  The reference carries Welford's (count, mean,
+                        // M2); the device carries the power sums (atomics cannot run Welford's recurrence) and forms
+                        // M2 = sum x^2 - (sum x)^2 / n here — equal up to rounding unless |mean| >> spread (tests state the bound)
+                        const double n = (double)((const unsigned long long*)op.a1)[s];
+                        const double s1 = ((const double*)op.a0)[s], s2 = ((const double*)op.b0)[s];
+                        const bool pop = op.kind == E_VAR_POP || op.kind == E_STD_POP;
+                        valid = pop ? n >= 1 : n >= 2;
+                        double m2 = s2 - s1 * s1 / n;
+                        if (m2 < 0) m2 = 0;
+                        double r = valid ? m2 / (pop ? n : n - 1) : __longlong_as_double(0x7ff8000000000000ll);
+                        if (valid && (op.kind == E_STD || op.kind == E_STD_POP)) r = sqrt(r);
+                        store_f_typed(op.out_data, op.out_ctype, p, r);
+                        break;
+                    }
+                    case E_SKEW: {  // skew_eval (groupby/_groupby_eval.h:110-137), same power sums as the reference
+                        const unsigned long long cnt = ((const unsigned long long*)op.a1)[s];
+                        const double n = (double)cnt, m1 = ((const double*)op.a0)[s], m2 = ((const double*)op.b0)[s], m3 = ((const double*)op.c0)[s];
+                        valid = cnt >= 3;
+                        double r = __longlong_as_double(0x7ff8000000000000ll);
+                        if (valid) {
+                            const double mean = m1 / n;
+                            const double num = m3 - 3.0 * m2 * mean + 2.0 * n * mean * mean * mean;
+                            const double den = pow(m2 - mean * m1, 1.5);
+                            if (num == 0.0 || fabs(den) < 1e-14 || isnan(den) || log2(fabs(den)) - log2(fabs(num)) < -20) r = 0.0;
+                            else r = (n * pow(n - 1, 1.5) / (n - 2)) * num / den / (n - 1);
+                        }
+                        store_f_typed(op.out_data, op.out_ctype, p, r);
                         break;
                     }
                     case K_MIN_I64: case K_MAX_I64: {
@@ -434,7 +474,7 @@ __device__ __forceinline__ void combine_apply(const CombineArgs& a, uint64_t slo
             unsigned long long v1 = a.a1[j] ? r[w++] : 0;
             switch (a.kinds[j]) {
                 case K_SUM_I64: case K_COUNT: case K_SIZE: atomicAdd((unsigned long long*)a.a0[j] + slot, v0); break;
-                case K_SUM_F64: atomicAdd((double*)a.a0[j] + slot, __longlong_as_double((long long)v0)); break;
+                case K_SUM_F64: case K_SUMSQ_F64: case K_SUMCUBE_F64: atomicAdd((double*)a.a0[j] + slot, __longlong_as_double((long long)v0)); break;
                 case K_MEAN:
                     atomicAdd((double*)a.a0[j] + slot, __longlong_as_double((long long)v0));
                     atomicAdd((unsigned long long*)a.a1[j] + slot, v1);
@@ -1571,6 +1611,15 @@ __global__ void __launch_bounds__(LC_THREADS, MIN_CTAS) groupby_lowcard_kernel(c
 // Host side
 // ================================================================================================
 
+// One user-visible aggregate: evaluated from the accumulators of `prim[0..n_prim)` (indices into the primitive list)
+struct OutSpec {
+    int ftype;
+    int kind;        // OpKind used by eval_output_kernel
+    int prim[3];
+    int n_prim;
+    int out_ctype, out_arrtype;
+};
+
 struct FuncSpec {
     int ftype;
     int in_col;  // physical input column or -1 (size)
@@ -1590,8 +1639,10 @@ class GroupbyState {
     cudaStream_t copy_stream = nullptr;
     int n_cols;
     std::vector<int8_t> c_types, arr_types;
-    int n_funcs;
+    int n_funcs;                  // primitive accumulator functions (what the kernels, the table and the exchange see)
     std::vector<FuncSpec> funcs;
+    int n_outs = 0;               // aggregates the caller asked for (output columns)
+    std::vector<OutSpec> outs;
     bool dropna, parallel;
     int n_pes, rank;
     int64_t output_batch_size;
@@ -1644,12 +1695,12 @@ class GroupbyState {
     GroupbyState(const int8_t* ct, const int8_t* at, int n_arrs, const int32_t* ftypes, const int32_t* f_in_offsets,
                  const int32_t* f_in_cols, int n_funcs_, uint64_t n_keys, int64_t out_bs, bool parallel_, bool dropna_,
                  int device_, int n_pes_, int rank_, int64_t expected_groups, cudaStream_t stream_)
-        : device(device_), stream(stream_), n_cols(n_arrs), n_funcs(n_funcs_), dropna(dropna_), parallel(parallel_),
+        : device(device_), stream(stream_), n_cols(n_arrs), n_funcs(0), n_outs(n_funcs_), dropna(dropna_), parallel(parallel_),
           n_pes(n_pes_), rank(rank_), output_batch_size(out_bs) {
         B200_REQUIRE(n_keys >= 1 && n_keys <= (uint64_t)MAX_KEYS, "b200 groupby: between 1 and 4 key columns are supported");
         nk = (int)n_keys;
         B200_REQUIRE(n_arrs >= 1, "b200 groupby: empty build schema");
-        B200_REQUIRE(n_funcs_ <= MAX_OPS, "b200 groupby: too many aggregate functions");
+        B200_REQUIRE(n_funcs_ <= 2 * MAX_OPS, "b200 groupby: too many aggregate functions");
         c_types.assign(ct, ct + n_arrs);
         arr_types.assign(at, at + n_arrs);
         B200_REQUIRE(n_arrs >= nk, "b200 groupby: fewer columns than keys");
@@ -1661,7 +1712,7 @@ class GroupbyState {
         if (!parallel) { n_pes = 1; rank = 0; }
         B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         sms = num_sms(device);
-        for (int j = 0; j < n_funcs; j++) {
+        for (int j = 0; j < n_outs; j++) {
             FuncSpec f{};
             f.ftype = ftypes[j];
             int n_in = f_in_offsets[j + 1] - f_in_offsets[j];
@@ -1695,14 +1746,40 @@ class GroupbyState {
                     else f.init0 = mn ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
                     break;
                 }
+                case FT_VAR: case FT_STD: case FT_VAR_POP: case FT_STD_POP: case FT_SKEW: {
+                    // composite: a K_MEAN pair (sum, count) + sum of squares (+ sum of cubes), all over the same input column
+                    OutSpec o{};
+                    o.ftype = f.ftype;
+                    o.kind = f.ftype == FT_VAR ? E_VAR : f.ftype == FT_STD ? E_STD : f.ftype == FT_VAR_POP ? E_VAR_POP : f.ftype == FT_STD_POP ? E_STD_POP : E_SKEW;
+                    o.out_ctype = CT_FLOAT64; o.out_arrtype = ARR_NULLABLE;
+                    const int kinds[3] = {K_MEAN, K_SUMSQ_F64, K_SUMCUBE_F64};
+                    o.n_prim = f.ftype == FT_SKEW ? 3 : 2;
+                    for (int q = 0; q < o.n_prim; q++) {
+                        FuncSpec pf = f;
+                        pf.kind = kinds[q]; pf.has_a1 = q == 0; pf.out_ctype = CT_FLOAT64; pf.out_arrtype = ARR_NULLABLE;
+                        // composites (and a plain mean) over the same input column share their accumulator columns
+                        int found = -1;
+                        for (int e = 0; e < (int)funcs.size(); e++)
+                            if (funcs[e].kind == pf.kind && funcs[e].in_col == pf.in_col) { found = e; break; }
+                        if (found < 0) { found = (int)funcs.size(); funcs.push_back(pf); }
+                        o.prim[q] = found;
+                    }
+                    outs.push_back(o);
+                    continue;
+                }
                 default:
                     throw Error("b200 groupby: unsupported aggregate function ftype=" + std::to_string(f.ftype) +
-                                " (supported: size, sum, count, mean, min, max)");
+                                " (supported: size, sum, count, mean, min, max, var, std, var_pop, std_pop, skew)");
             }
+            OutSpec o{};
+            o.ftype = f.ftype; o.kind = f.kind; o.prim[0] = (int)funcs.size(); o.n_prim = 1; o.out_ctype = f.out_ctype; o.out_arrtype = f.out_arrtype;
+            outs.push_back(o);
             funcs.push_back(f);
         }
+        n_funcs = (int)funcs.size();
+        B200_REQUIRE(n_funcs <= MAX_OPS, "b200 groupby: too many aggregate functions (composite ones count their accumulator columns)");
         d_a0.resize(n_funcs); d_a1.resize(n_funcs);
-        d_out_data.resize(n_funcs); d_out_valid.resize(n_funcs);
+        d_out_data.resize(n_outs); d_out_valid.resize(n_outs);
         d_counters.alloc(8 * sizeof(long long));
         B200_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(long long), stream));
         h_counters = (long long*)pinned_acquire(8 * sizeof(long long));
@@ -2356,13 +2433,16 @@ class GroupbyState {
             eval_mk_keys_kernel<<<grid_for(max_out), 256, 0, stream>>>(k);
             launches++;
         }
-        e.n_ops = n_funcs;
-        for (int j = 0; j < n_funcs; j++) {
-            const FuncSpec& f = funcs[j];
+        e.n_ops = n_outs;
+        for (int j = 0; j < n_outs; j++) {
+            const OutSpec& o = outs[j];
+            const int p0 = o.prim[0];
             d_out_data[j].ensure((size_t)(max_out + 32) * 8);
-            e.ops[j].kind = f.kind; e.ops[j].out_ctype = f.out_ctype; e.ops[j].a0 = d_a0[j].p;
-            e.ops[j].a1 = f.has_a1 ? d_a1[j].p : nullptr; e.ops[j].out_data = d_out_data[j].p;
-            if (f.out_arrtype == ARR_NULLABLE) { d_out_valid[j].ensure(words * 4); e.ops[j].out_valid = d_out_valid[j].as<uint32_t>(); }
+            e.ops[j].kind = o.kind; e.ops[j].out_ctype = o.out_ctype; e.ops[j].a0 = d_a0[p0].p;
+            e.ops[j].a1 = funcs[p0].has_a1 ? d_a1[p0].p : nullptr; e.ops[j].out_data = d_out_data[j].p;
+            e.ops[j].b0 = o.n_prim > 1 ? d_a0[o.prim[1]].p : nullptr;
+            e.ops[j].c0 = o.n_prim > 2 ? d_a0[o.prim[2]].p : nullptr;
+            if (o.out_arrtype == ARR_NULLABLE) { d_out_valid[j].ensure(words * 4); e.ops[j].out_valid = d_out_valid[j].as<uint32_t>(); }
         }
         eval_output_kernel<<<grid_for(max_out), 256, 0, stream>>>(e);
         launches++;
@@ -2556,7 +2636,7 @@ class GroupbyState {
         if (bs % 32 != 0 && bs < n_out) bs = (bs + 31) & ~31ll;  // validity bitmaps are sliced at word granularity
         int64_t rows = produce_output ? std::min(bs, n_out - out_cursor) : 0;
         B200_REQUIRE(out->cols != nullptr, "b200 groupby: out->cols must point to n_keys + n_funcs descriptors");
-        out->n_rows = rows; out->n_cols = nk + n_funcs; out->device = device;
+        out->n_rows = rows; out->n_cols = nk + n_outs; out->device = device;
         int64_t off = out_cursor;
         for (int kc = 0; kc < nk; kc++) {
             b200_column& k = out->cols[kc];
@@ -2566,11 +2646,11 @@ class GroupbyState {
             k.validity = arr_types[kc] == ARR_NULLABLE ? kv.as<uint8_t>() + off / 8 : nullptr;
             k.length = rows; k.c_type = c_types[kc]; k.arr_type = arr_types[kc];
         }
-        for (int j = 0; j < n_funcs; j++) {
+        for (int j = 0; j < n_outs; j++) {
             b200_column& c = out->cols[nk + j];
-            c.data = (char*)d_out_data[j].p + off * ctype_size(funcs[j].out_ctype);
-            c.validity = funcs[j].out_arrtype == ARR_NULLABLE ? d_out_valid[j].as<uint8_t>() + off / 8 : nullptr;
-            c.length = rows; c.c_type = funcs[j].out_ctype; c.arr_type = funcs[j].out_arrtype;
+            c.data = (char*)d_out_data[j].p + off * ctype_size(outs[j].out_ctype);
+            c.validity = outs[j].out_arrtype == ARR_NULLABLE ? d_out_valid[j].as<uint8_t>() + off / 8 : nullptr;
+            c.length = rows; c.c_type = outs[j].out_ctype; c.arr_type = outs[j].out_arrtype;
         }
         out_cursor += rows;
         *out_is_last = out_cursor >= n_out ? 1 : 0;

@@ -321,3 +321,36 @@ def test_float32_sum_mean_stated_tolerance(gpu_lib, oracle):
     # one float32 rounding of the exact sum
     assert (np.abs(got["f0"].to_numpy().astype(np.float64) - exact) <= 2.0 ** -24 * np.abs(exact) * 1.0000001).all()
     np.testing.assert_allclose(got["f1"].to_numpy(), exact / cnt, rtol=1e-12)  # MEAN is float64 throughout (mean_agg :673-689)
+
+
+@pytest.mark.parametrize("nullable", [False, True])
+def test_var_std_skew_against_pandas_and_reference_formulas(gpu_lib, nullable):
+    """var / std / var_pop / std_pop / skew (Bodo_FTypes 24 / 25 / 22 / 23 / 27; the reference's GPU test matrix,
+    bodo/tests/test_df_lib/test_gpu/test_gpu_end_to_end.py:68-110).  Reference: Welford (count, mean, M2) for var / std
+    (groupby/_groupby_agg_funcs.h:694-719), power sums for skew (:723-745), eval in _groupby_eval.h:71-137.  The device carries
+    power sums for all of them; tolerance = the reference's test tolerance (rtol 1e-5), valid while |mean| / std <~ 1e5
+    (cancellation in sum x^2 - (sum x)^2 / n loses about 2 log10(|mean| / std) digits of the 16 a double has)."""
+    rng = np.random.default_rng(23)
+    n, ng = 60_000, 211
+    k = rng.integers(0, ng, n).astype(np.int64)
+    k[:3] = [ng, ng + 1, ng + 1]  # groups with one / two rows: var NaN for n < 2, skew NaN for n < 3
+    x = rng.standard_normal(n) * 3.0 + 10.0
+    i = rng.integers(-1000, 1000, n).astype(np.int64)
+    df = pd.DataFrame({"k": k, "x": x, "i": i})
+    if nullable:
+        df["x"] = pd.array(x, dtype="Float64")
+        df["i"] = pd.array(i, dtype="Int64")
+        df.loc[rng.random(n) < 0.07, "x"] = pd.NA
+        df.loc[rng.random(n) < 0.07, "i"] = pd.NA
+    t = Table.from_pandas(df)
+    fn = ("var", "std", "skew", "var_pop", "std_pop", "var", "skew", "mean")
+    cols = (1, 1, 1, 1, 1, 2, 2, 1)
+    got = positional(stream_groupby(t, (0,), fn, tuple(range(len(fn) + 1)), cols, batch_size=7000, to_device=True)).sort_values("key").reset_index(drop=True)
+    g = df.astype({"x": "float64", "i": "float64"}).groupby("k")
+    exp = pd.DataFrame({"key": sorted(df.k.unique()), "f0": g.x.var().to_numpy(), "f1": g.x.std().to_numpy(), "f2": g.x.skew().to_numpy(),
+                        "f3": g.x.var(ddof=0).to_numpy(), "f4": g.x.std(ddof=0).to_numpy(), "f5": g.i.var().to_numpy(),
+                        "f6": g.i.skew().to_numpy(), "f7": g.x.mean().to_numpy()})
+    assert len(got) == len(exp)
+    for c in exp.columns[1:]:
+        np.testing.assert_allclose(got[c].to_numpy(dtype="float64", na_value=np.nan), exp[c].to_numpy(dtype="float64"), rtol=1e-5, atol=1e-8,
+                                   equal_nan=True, err_msg=c)
