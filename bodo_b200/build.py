@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbodo_b200.so")
-SOURCES = ["misc.cu", "groupby.cu", "shuffle.cu", "join.cu"]
+SOURCES = ["misc.cu", "groupby.cu", "shuffle.cu", "join.cu", "expr.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",

@@ -94,6 +94,113 @@ class PhysicalReadParquet:
         return Table.from_arrow(cur), (OperatorResult.FINISHED if self._next is None else OperatorResult.HAVE_MORE_OUTPUT)
 
 
+def _infer_ctype(e, col_ctypes: dict) -> int:
+    """Storage type of an expression's value: a bare column keeps its type, arithmetic is FLOAT64 as soon as a float (or a
+    true division) is involved and INT64 otherwise, comparisons / logic are BOOL."""
+    from .table import CTypes
+
+    if e.op == "col":
+        return col_ctypes[e.value]
+    if e.op == "const_i64":
+        return CTypes.INT64
+    if e.op == "const_f64" or e.op in ("div", "to_f64"):
+        return CTypes.FLOAT64
+    if e.op in ("lt", "le", "gt", "ge", "eq", "ne", "and", "or", "not", "is_null"):
+        return CTypes.BOOL
+    if e.op == "to_i64":
+        return CTypes.INT64
+    kinds = [_infer_ctype(a, col_ctypes) for a in e.args]
+    return CTypes.FLOAT64 if any(k in (CTypes.FLOAT64, CTypes.FLOAT32) for k in kinds) else CTypes.INT64
+
+
+class PhysicalFilterProject:
+    """Filter + projection in one device pass (bodo/pandas/physical/filter.h + project.h with their expression trees,
+    expression.{h,cpp}): `predicate` (bodo_b200.expr.Expr or None) selects rows, `outputs` = [(name, Expr)] are the columns of
+    the result (col("x") passes a column through).  Host batches are staged to the device first; the result is a device batch."""
+
+    def __init__(self, predicate, outputs, device: int | None = None, stream: int = 0):
+        self.predicate = predicate
+        self.outputs = list(outputs)
+        self.device = device
+        self.stream = stream
+        self._compiled = None
+
+    def _compile(self, batch: Table):
+        from . import _lib
+        from .expr import compile_program
+
+        col_index = {n: i for i, n in enumerate(batch.names)}
+        col_ctypes = {n: c.c_type for n, c in zip(batch.names, batch.columns)}
+        exprs = ([self.predicate] if self.predicate is not None else []) + [e for _, e in self.outputs]
+        prog, starts = compile_program(exprs, col_index)
+        ffi = _lib.ffi
+        cprog = ffi.new("b200_expr_instr[]", len(prog))
+        for i, (op, arg) in enumerate(prog):
+            cprog[i].op = op
+            cprog[i].arg = arg
+        pred_start = starts[0] if self.predicate is not None else -1
+        out_starts = starts[1:] if self.predicate is not None else starts
+        out_ct = [_infer_ctype(e, col_ctypes) for _, e in self.outputs]
+        self._compiled = (cprog, len(prog), pred_start, ffi.new("int32_t[]", out_starts or [0]), out_ct)
+
+    def ProcessBatch(self, batch: Table, prev: OperatorResult):
+        import torch
+
+        from . import _lib
+        from .streaming.dist_join import to_device
+        from .table import ArrTypes, Column, CTable, np_dtype_of
+
+        dev_i = self.device if self.device is not None else (batch.device if batch.device >= 0 else torch.cuda.current_device())
+        batch = to_device(batch, dev_i)
+        if self._compiled is None:
+            self._compile(batch)
+        cprog, n_instr, pred_start, out_starts, out_ct = self._compiled
+        dev = torch.device("cuda", dev_i)
+        n = batch.n_rows
+        cols = []
+        for ct in out_ct:
+            dt = getattr(torch, str(np_dtype_of(ct)))
+            cols.append(Column(torch.empty(max(n, 1), dtype=dt, device=dev), torch.zeros((n + 31) // 32 * 4 + 8, dtype=torch.uint8, device=dev), ct,
+                               ArrTypes.NULLABLE_INT_BOOL, n))
+        out = Table(cols, [nm for nm, _ in self.outputs])
+        cin, cout = CTable(batch), CTable(out)
+        L, ffi = _lib.lib(), _lib.ffi
+        kept = _lib.check(int(L.b200_filter_project(cin.ptr, cprog, n_instr, pred_start, out_starts, len(out_ct), cout.ptr, ffi.cast("void*", self.stream))),
+                          "filter + projection")
+        res = Table([Column(c.data[:kept], c.validity, c.c_type, c.arr_type, kept) for c in cols], list(out.names))
+        return res, (OperatorResult.FINISHED if prev == OperatorResult.FINISHED else OperatorResult.NEED_MORE_INPUT)
+
+
+class PhysicalReadArrowDevice:
+    """Source over an in-memory pyarrow Table that hands out DEVICE batches; string columns named in `dict_builders`
+    ({column: DictionaryBuilder}) travel as dictionary ids unified against the builder (bodo_b200.dictionary), everything else
+    as its fixed-width Arrow buffers (the H2D half of the reference's convertTableToGPU, bodo/pandas/physical/operator.cpp:293-380)."""
+
+    def __init__(self, table, batch_size: int = STREAMING_BATCH_SIZE, device: int = 0, dict_builders: dict | None = None):
+        self.arrow = table.combine_chunks()
+        self.batch_size = batch_size
+        self.device = device
+        self.dict_builders = dict_builders or {}
+        self.cur = 0
+
+    def ProduceBatch(self):
+        from .streaming.dist_join import to_device
+
+        n = self.arrow.num_rows
+        sl = self.arrow.slice(self.cur, self.batch_size)
+        self.cur += self.batch_size
+        plain = [nm for nm in sl.schema.names if nm not in self.dict_builders]
+        t = to_device(Table.from_arrow(sl.select(plain)), self.device) if plain else Table([], [])
+        cols, names = [], []
+        for nm in sl.schema.names:
+            if nm in self.dict_builders:
+                cols.append(self.dict_builders[nm].unify(sl.column(nm), self.device))
+            else:
+                cols.append(t.columns[plain.index(nm)])
+            names.append(nm)
+        return Table(cols, names), (OperatorResult.FINISHED if self.cur >= n else OperatorResult.HAVE_MORE_OUTPUT)
+
+
 class PhysicalAggregate:
     """Groupby sink/source (aggregate.h:65-365). `aggs` = [(func_name, input_column_index or None for size)]."""
 

@@ -101,3 +101,22 @@ def test_unsupported_inputs_fail_loudly():
         init_groupby_state(-1, (0,), ("sum",), (0, 1), (1,), mrnf_sort_col_inds=(1,))
     with pytest.raises(TypeError, match="object dtype|unsupported"):
         Table.from_pandas(pd.DataFrame({"s": ["a", "b"]}))
+
+
+def test_expression_programs_and_dictionary_decode_host_logic():
+    import datetime
+    import struct
+
+    from bodo_b200.dictionary import DictionaryBuilder
+    from bodo_b200.expr import OPS, col, compile_program, lit
+    e = (col("a") * (lit(1.0) - col("b")) <= 3) & ~col("d").isnull()
+    prog, starts = compile_program([e, col("d"), lit(datetime.date(1970, 1, 11))], {"a": 0, "b": 1, "d": 2})
+    assert starts == [0, 12, 14] and prog[-1] == (OPS["end"], 0) and prog[-2] == (OPS["const_i64"], 10)
+    ops = [o for o, _ in prog[:12]]
+    assert ops == [OPS[x] for x in ("col", "const_f64", "col", "sub", "mul", "const_i64", "le", "col", "is_null", "not", "and", "end")]
+    assert prog[1][1] == struct.unpack("<q", struct.pack("<d", 1.0))[0] and e.columns() == {"a", "b", "d"}
+    with pytest.raises(KeyError):
+        compile_program([col("zz")], {"a": 0})
+    b = DictionaryBuilder()
+    b.values, b.index = ["N", "R"], {"N": 0, "R": 1}
+    assert list(b.decode(np.array([1, 0, 1]), np.array([True, True, False]))) == ["R", "N", None]
