@@ -2330,6 +2330,8 @@ class GroupbyState {
             B200_REQUIRE(t->cols[c].c_type == c_types[c], "b200 groupby: batch column dtype differs from the build schema");
             B200_REQUIRE(n == 0 || t->cols[c].data != nullptr, "b200 groupby: null data pointer");
         }
+        if (coalesce(t, n)) return;  // small batch of the fast-path signature: buffered until a launch is worth it
+        flush_coalesced();
         if (t->device >= 0) {
             B200_REQUIRE(t->device == device, "b200 groupby: batch lives on a different device than the state");
             for (int64_t r0 = 0; r0 < n; r0 += CHUNK_ROWS) {
@@ -2385,6 +2387,51 @@ class GroupbyState {
         }
     }
 
+    // ---- coalescing of small streaming batches ----
+    // The reference streams 32 768-row batches (bodo/libs/streaming/_shuffle.h:27-31); the SM-partitioned and low-cardinality
+    // kernels want >= 2^20 rows per launch.  Batches of the fast-path signature (non-null int64 key, SUM / COUNT / SIZE over one
+    // non-null int64 value column) below that size are appended to a device-side buffer (one D2D or H2D copy per column) and
+    // consumed together when the buffer is full, when a batch of another shape arrives, or when the build ends.
+    static constexpr int64_t CO_MIN_BATCH = 1ll << 20, CO_ROWS = 1ll << 22;
+    DevBuf co_key, co_val;
+    int64_t co_n = 0, co_batches = 0;
+    int co_vcol = -1;
+    bool coalesce(const b200_table* t, int64_t n) {
+        if (n == 0 || n >= CO_MIN_BATCH || nk != 1 || n_funcs < 1 || c_types[0] != CT_INT64 || t->cols[0].validity != nullptr) return false;
+        { const char* e = getenv("B200_COALESCE"); if (e && e[0] == '0') return false; }
+        int vcol = -1;
+        for (auto& f : funcs) {
+            if (f.kind == K_SIZE) continue;
+            if (!((f.kind == K_SUM_I64 || f.kind == K_COUNT) && f.in_ctype == CT_INT64 && t->cols[f.in_col].validity == nullptr)) return false;
+            if (vcol >= 0 && vcol != f.in_col) return false;
+            vcol = f.in_col;
+        }
+        if (!spg_probe()) return false;
+        if (co_n > 0 && (co_vcol != vcol || co_n + n > CO_ROWS)) flush_coalesced();
+        co_vcol = vcol;
+        co_key.ensure((size_t)CO_ROWS * 8);
+        if (vcol >= 0) co_val.ensure((size_t)CO_ROWS * 8);
+        const cudaMemcpyKind kind = t->device >= 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (t->device >= 0) B200_REQUIRE(t->device == device, "b200 groupby: batch lives on a different device than the state");
+        B200_CUDA(cudaMemcpyAsync(co_key.as<long long>() + co_n, t->cols[0].data, (size_t)n * 8, kind, stream));
+        if (vcol >= 0) B200_CUDA(cudaMemcpyAsync(co_val.as<long long>() + co_n, t->cols[vcol].data, (size_t)n * 8, kind, stream));
+        if (kind == cudaMemcpyHostToDevice) B200_CUDA(cudaStreamSynchronize(stream));  // the caller may reuse its host batch right away
+        co_n += n;
+        co_batches++;
+        if (co_n + CO_MIN_BATCH > CO_ROWS) flush_coalesced();
+        return true;
+    }
+    void flush_coalesced() {
+        if (co_n == 0) return;
+        std::vector<const void*> data(n_cols, nullptr);
+        std::vector<const uint8_t*> valid(n_cols, nullptr);
+        data[0] = co_key.p;
+        if (co_vcol >= 0) data[co_vcol] = co_val.p;
+        const int64_t n = co_n;
+        co_n = 0;
+        consume_device_chunk(data, valid, n);
+    }
+
     // ---- finalize ----
     // Compacts the occupied slots (owned_only: of the groups this rank owns).  No host synchronisation: the output is sized by
     // the table's group limit (cap / 2 + the two special slots), the count stays on the device (counters[2]).
@@ -2410,6 +2457,7 @@ class GroupbyState {
         double tf0 = now();
         struct Acc3 { double& t; double t0; ~Acc3() { t += now() - t0; } } acc3{t_finalize, tf0};
         B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
+        flush_coalesced();
         compact(/*owned_only=*/parallel && n_pes > 1);
         const int64_t max_out = max_out_bound();
         EvalArgs e{};
@@ -2511,6 +2559,7 @@ class GroupbyState {
     int64_t xchg_row_bytes() const { return (int64_t)((nk == 1 ? 2 : nk + 1) + acc_count()) * 8; }
     void exchange_fused_pack(void* const* peer_slabs_dev, int64_t cap_rows) {
         B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
+        flush_coalesced();
         build_done = true;
         d_xchg_cursors.ensure((size_t)std::max(n_pes, 32) * 8);
         B200_CUDA(cudaMemsetAsync(d_xchg_cursors.p, 0, (size_t)std::max(n_pes, 32) * 8, stream));
@@ -2562,6 +2611,7 @@ class GroupbyState {
     int64_t shuffle_prepare(int64_t* send_counts) {
         B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         B200_REQUIRE(nk == 1, "b200 groupby: multi-column keys on the sharded path use the fused exchange (symmetric memory); the NCCL form handles single-column keys");
+        flush_coalesced();
         build_done = true;
         compact(/*owned_only=*/false);
         read_counters();
@@ -2765,6 +2815,7 @@ int64_t b200_groupby_get_metric(void* state, int32_t which) {
         case 8: return s->spg_launches;
         case 9: return s->spg_retry_rows;
         case 10: return s->lc_launches;
+        case 11: return s->co_batches;
         case 100: s->profiling = true; return 0;
         default: return -1;
     }

@@ -126,7 +126,8 @@ void b200_delete_groupby_state(void* state);
  * 2 rows consumed, 3 table rebuilds, 4 kernel launches so far, 5 rows replayed from the fail list,
  * 6 accumulated device time of the consume kernel in microseconds (CUDA events on the state's stream;
  * only when profiling was enabled by querying metric 100 first), 7 consume-kernel launches, 8 SM-partitioned
- * (SPG) launches, 9 rows/partials replayed from the SPG retry lists, 10 low-cardinality (LC) launches. */
+ * (SPG) launches, 9 rows/partials replayed from the SPG retry lists, 10 low-cardinality (LC) launches, 11 small batches
+ * that were coalesced on the device before a fast-path launch. */
 int64_t b200_groupby_get_metric(void* state, int32_t which);
 
 /* ---- streaming hash join (reference: bodo/libs/streaming/_join.cpp) ---- */

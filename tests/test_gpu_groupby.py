@@ -354,3 +354,26 @@ def test_var_std_skew_against_pandas_and_reference_formulas(gpu_lib, nullable):
     for c in exp.columns[1:]:
         np.testing.assert_allclose(got[c].to_numpy(dtype="float64", na_value=np.nan), exp[c].to_numpy(dtype="float64"), rtol=1e-5, atol=1e-8,
                                    equal_nan=True, err_msg=c)
+
+
+@pytest.mark.parametrize("to_device", [False, True])
+def test_streaming_batches_are_coalesced_into_fast_path_launches(gpu_lib, oracle, to_device):
+    """The reference's streaming batch size is 32 768 rows (bodo/libs/streaming/_shuffle.h:27-31): such batches are buffered on the
+    device and reach the SM-partitioned / low-cardinality kernels in >= 2^20-row launches (metric 8 / 10 > 0, metric 11 counts the
+    coalesced batches); result bit-exact against the oracle."""
+    from bodo_b200.streaming.groupby import (delete_groupby_state, get_metric, groupby_build_consume_batch, groupby_produce_output_batch,
+                                             init_groupby_state)
+    from tests.helpers import table_to_device
+    n, ng, bs = 3_000_000 + 12_345, 40_000, 32_768
+    k, v = oracle.synth_fill(0, n, ng, 31)
+    t = Table.from_pandas(pd.DataFrame({"k": k, "v": v}))
+    st = init_groupby_state(-1, (0,), ("sum", "count"), (0, 1, 2), (1, 1), output_batch_size=1 << 30)
+    for r0 in range(0, n, bs):
+        b = t.slice(r0, r0 + bs)
+        groupby_build_consume_batch(st, table_to_device(b) if to_device else b, r0 + bs >= n, True)
+    out, last = groupby_produce_output_batch(st, True)
+    got = out.to_pandas()
+    fast_launches, coalesced = get_metric(st, 8) + get_metric(st, 10), get_metric(st, 11)
+    delete_groupby_state(st)
+    assert coalesced >= 90 and fast_launches >= 1, (coalesced, fast_launches)
+    assert_frames_equal(positional(got), oracle_groupby_frame(oracle, t, 0, ["sum", "count"], [1, 1]))
