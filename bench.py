@@ -56,6 +56,11 @@ def parse_args():
     ap.add_argument("--ref-sample-rows", type=int, default=512_000_000)
     # --workload join: BASELINE.json configs[2] (benchmarks/join_bench.py); the default workload is the contract's configs[1] / [3]
     ap.add_argument("--workload", default="groupby", choices=["groupby", "join"])
+    ap.add_argument("--aggs", default="sum,count", help="groupby aggregate functions; anything but sum,count runs the variant bench")
+    ap.add_argument("--nullable", action="store_true", help="groupby variant: nullable key (1 %% NA) and value (10 %% NA) columns")
+    ap.add_argument("--key-dtype", default="int64", choices=["int64", "int32"])
+    ap.add_argument("--val-dtype", default="int64", choices=["int64", "int32"])
+    ap.add_argument("--no-hint", action="store_true", help="do not pass the exact cardinality as expected_groups")
     ap.add_argument("--build-rows", type=int, default=100_000_000)
     ap.add_argument("--probe-rows", type=int, default=1_000_000_000)
     ap.add_argument("--probe-batch", type=int, default=250_000_000)
@@ -205,6 +210,11 @@ def main():
     if args.impl == "reference":
         reference_arm(args)
         return
+    if args.aggs.replace(" ", "") != "sum,count" or args.nullable or args.key_dtype != "int64" or args.val_dtype != "int64":
+        from benchmarks import groupby_variant_bench
+
+        groupby_variant_bench.run(args, ClockSampler, peaks)
+        return
 
     import numpy as np
     import torch
@@ -237,12 +247,13 @@ def main():
     torch.cuda.synchronize(dev)
     expect_sum = int(vals.sum().item())  # wraps like the int64 SUM does
     table = Table([Column(keys), Column(vals)], ["key", "val"])
-    exp_groups_local = args.groups
+    exp_groups_local = 0 if args.no_hint else args.groups
 
     stats = {}
 
-    def one_step(tab, collect=False, profile=False, to_host=False):
-        st = G.init_groupby_state(-1, (0,), ("sum", "count"), (0, 1, 2), (1, 1), parallel=world > 1, expected_groups=exp_groups_local,
+    def one_step(tab, collect=False, profile=False, to_host=False, hint=None):
+        st = G.init_groupby_state(-1, (0,), ("sum", "count"), (0, 1, 2), (1, 1), parallel=world > 1,
+                                  expected_groups=exp_groups_local if hint is None else hint,
                                   output_batch_size=1 << 40, device=local_rank, stream=stream_ptr)
         st._ensure(tab)
         if profile:
@@ -322,6 +333,22 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
+
+    # the same steps WITHOUT the expected_groups hint (the reference's API has no such argument: a drop-in caller gets this
+    # route — the state learns the cardinality from a 2^20-row prefix through the direct kernel, then takes the same kernels)
+    barrier()
+    nh0, nh1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    one_step(table, hint=0)
+    barrier()
+    nh0.record(stream)
+    for _ in range(args.steps):
+        one_step(table, hint=0)
+    nh1.record(stream)
+    barrier()
+    nh = torch.tensor([nh0.elapsed_time(nh1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(nh, op=dist.ReduceOp.MAX)
+    no_hint_ms = float(nh[0].item())
 
     # untimed: one profiled step (per-launch CUDA events inside the library) + result check
     one_step(table, collect=True, profile=True)
@@ -405,6 +432,9 @@ def main():
             "config": {"workload": workload_name(args), "rows": args.rows, "groups": args.groups, "aggs": ["sum", "count"],
                        "rows_per_gpu": n_local, "l2": "inputs (16 B/row x rows_per_gpu) exceed the 126 MB L2; no flush needed",
                        "step": "init state + consume + exchange + finalize + produce", "result_groups": n_groups_total,
+                       "expected_groups_hint": exp_groups_local,
+                       "no_hint": {"value": args.rows * args.steps / (no_hint_ms * 1e-3), "ms_per_step": no_hint_ms / args.steps,
+                                   "note": "same steps with expected_groups=0 (what a caller of the reference's API passes)"},
                        "result_check": ("per-group ok: every group's SUM and COUNT equal an independent device recomputation over all ranks' rows"
                                         + ("; every group sits on hash_to_rank(key)" if world > 1 else "")) if check_ok else "MISMATCH"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,

@@ -1504,6 +1504,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     }
 }
 
+#include "spgg.cuh"  // SPG-G: the same two kernels for nullable / 4-byte / mean / min / max signatures
 #include "spf.cuh"  // SPF: the fused persistent variant of the SM-partitioned path (one kernel, bucket hand-off through L2)
 
 // ---- low-cardinality kernel (LC): every CTA keeps a private shared-memory table of ALL groups ----------------
@@ -2009,6 +2010,26 @@ class GroupbyState {
             }
         }
         { const char* e2 = getenv("B200_SPG_TMA"); spg_use_tma = !(e2 && e2[0] == '0'); }
+        {   // SPG-G (spgg.cuh): generic signatures
+            spgg_enabled = 2 * sms <= GEN_CLS;  // classes of K1g's counting sort: at least owners + owners
+            const void* gp[6] = {(const void*)spgg_partition_kernel<8, 8>, (const void*)spgg_partition_kernel<8, 4>, (const void*)spgg_partition_kernel<8, 0>,
+                                 (const void*)spgg_partition_kernel<4, 8>, (const void*)spgg_partition_kernel<4, 4>, (const void*)spgg_partition_kernel<4, 0>};
+            for (auto f : gp)
+                if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_K1_SMEM) != cudaSuccess) { cudaGetLastError(); spgg_enabled = false; }
+            for (int v = 0; v < 4; v++) {  // v = mm + 2 * nn
+                const int sb = 16 + ((v & 1) ? 16 : 0) + ((v & 2) ? 4 : 0);
+                spgg_ns[v] = ((int)(((size_t)max_smem - 64) / sb) - SPG_STASH) & ~1;
+                spgg_smem[v] = (size_t)(spgg_ns[v] + SPG_STASH) * sb + 16;
+            }
+            const void* ga[8] = {(const void*)spgg_aggregate_kernel<false, false, false>, (const void*)spgg_aggregate_kernel<true, false, false>,
+                                 (const void*)spgg_aggregate_kernel<false, true, false>, (const void*)spgg_aggregate_kernel<true, true, false>,
+                                 (const void*)spgg_aggregate_kernel<false, false, true>, (const void*)spgg_aggregate_kernel<true, false, true>,
+                                 (const void*)spgg_aggregate_kernel<false, true, true>, (const void*)spgg_aggregate_kernel<true, true, true>};
+            for (int q = 0; q < 8; q++)  // q = sum + 2 * mm + 4 * nn
+                if (cudaFuncSetAttribute(ga[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spgg_smem[q >> 1]) != cudaSuccess) { cudaGetLastError(); spgg_enabled = false; }
+            const char* e7 = getenv("B200_SPG_GEN");
+            if (e7 && e7[0] == '0') spgg_enabled = false;
+        }
         if (cudaFuncSetAttribute((const void*)spg_hot_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPG_HOT_SAMPLE_SMEM) != cudaSuccess) { cudaGetLastError(); return false; }
         { const char* e4 = getenv("B200_SPG_HOT"); spg_hot_enabled = !(e4 && e4[0] == '0'); }
         d_hot.alloc((size_t)SPG_HOT_SLOTS * 8 + 16);
@@ -2018,12 +2039,16 @@ class GroupbyState {
             if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)LC_SLOTS_BIG * 20 + 64)) != cudaSuccess) { cudaGetLastError(); return false; }
         { const char* e3 = getenv("B200_LC"); lc_enabled = !(e3 && e3[0] == '0'); }
         spg_owners = sms;  // one owner (bucket + shared table) per SM
-        d_bucket_cnt.alloc((size_t)spg_owners * SPG_CNT_STRIDE * 8);
+        d_bucket_cnt.alloc((size_t)std::max(2 * spg_owners, GEN_CLS) * SPG_CNT_STRIDE * 8);  // SPG-G: one counter per class of K1g
         spg_state = 1;
         return true;
     }
 
     bool spg_use_tma = true, lc_enabled = true, lowcard_small = false;
+    int spgg_ns[4] = {0, 0, 0, 0};  // K2g table slots, by slot layout v = (min/max fields) + 2 * (NA-value counter)
+    size_t spgg_smem[4] = {0, 0, 0, 0};
+    bool spgg_enabled = true;      // B200_SPG_GEN=0 disables the generic SM-partitioned path
+    int64_t spgg_launches = 0;
     int spg_n_hot = 0;
     bool spg_static = false;   // B200_SPG_STATIC=1
     bool spg_onepass = false;  // B200_SPG_ONEPASS=1
@@ -2218,6 +2243,126 @@ class GroupbyState {
         n_groups_bound = n_groups;
     }
 
+    // ---- SPG-G: the SM-partitioned path for generic signatures (spgg.cuh) ----
+    struct GenSig { int vcol = -1; bool has_sum = false, has_mm = false, has_nn = false; int layout = 0; };
+    static bool gen_int_ok(int ct) { const int sz = ctype_size(ct); return (sz == 4 || sz == 8) && !ctype_is_float(ct) && ct != CT_UINT64; }
+    bool gen_signature(const std::vector<const void*>& data, const std::vector<const uint8_t*>& valid, GenSig& gs) const {
+        if (nk != 1 || n_funcs < 1 || n_funcs > GEN_MAX_F || !gen_int_ok(c_types[0])) return false;
+        bool has_size = false;
+        for (auto& f : funcs) {
+            switch (f.kind) {
+                case K_SIZE: has_size = true; continue;
+                case K_COUNT: break;
+                case K_SUM_I64: case K_MEAN: gs.has_sum = true; break;
+                case K_MIN_I64: case K_MAX_I64: gs.has_mm = true; break;
+                default: return false;
+            }
+            if (!gen_int_ok(f.in_ctype)) return false;
+            if (gs.vcol >= 0 && gs.vcol != f.in_col) return false;
+            gs.vcol = f.in_col;
+        }
+        // tiles (columns and validity bitmaps) are fetched with TMA bulk copies: 16-byte aligned sources
+        if (((uintptr_t)data[0] & 15) || ((uintptr_t)valid[0] & 15)) return false;
+        if (gs.vcol >= 0 && (((uintptr_t)data[gs.vcol] & 15) || ((uintptr_t)valid[gs.vcol] & 15))) return false;
+        gs.has_nn = gs.vcol >= 0 && valid[gs.vcol] != nullptr && has_size;
+        gs.layout = (gs.has_mm ? 1 : 0) + (gs.has_nn ? 2 : 0);
+        return true;
+    }
+    int64_t spgg_group_capacity(int layout) const { return (int64_t)spg_owners * (spgg_ns[layout] * 7 / 10); }
+    int spgg_pass_count(int64_t est, int layout) const {
+        int64_t p = (est + spgg_group_capacity(layout) - 1) / spgg_group_capacity(layout);
+        return p <= 1 ? 1 : (p <= SPG_MAX_PASSES ? (int)p : 0);
+    }
+    static constexpr int64_t GEN_LAUNCH_ROWS = 1ll << 27;
+    PooledBuf d_nbucket;  // key-only buckets of the rows whose value is NA
+
+    void consume_spg_gen(const std::vector<const void*>& data, const std::vector<const uint8_t*>& valid, int64_t n, const GenSig& gs, int passes) {
+        double tspg0 = now();
+        struct Acc2 { double& t; double t0; ~Acc2() { t += now() - t0; } } acc2{t_spg, tspg0};
+        const int kct = c_types[0], vct = gs.vcol >= 0 ? c_types[gs.vcol] : CT_INT64;
+        const int ks = ctype_size(kct), vs = gs.vcol >= 0 ? ctype_size(vct) : 0;
+        const int mm = gs.layout;
+        const bool v_nullable = gs.vcol >= 0 && valid[gs.vcol] != nullptr;
+        // multi-pass: K1g partitions straight into owners x passes buckets when its class table has room for them
+        const int n_vo = (passes > 1 && spg_owners * passes + (v_nullable ? spg_owners : 0) <= GEN_CLS) ? spg_owners * passes : spg_owners;
+        for (int64_t r0 = 0; r0 < n; r0 += GEN_LAUNCH_ROWS) {
+            const int64_t rows = std::min(GEN_LAUNCH_ROWS, n - r0);
+            // a bucket holds rows / owners rows (NA-value buckets: at most that) however many buckets the valued rows spread over
+            const int64_t bucket_cap = (rows / spg_owners) + (rows / spg_owners) / 8 + 4096;
+            double ta = now();
+            d_bucket.ensure(device, (size_t)n_vo * bucket_cap * 16);
+            if (v_nullable) d_nbucket.ensure(device, (size_t)spg_owners * bucket_cap * 8);
+            d_retry2[0].ensure(device, ((size_t)rows + (size_t)spg_owners * (spgg_ns[mm] + SPG_STASH) * passes) * GEN_RETRY_WORDS * 8);
+            t_alloc += now() - ta;
+            B200_CUDA(cudaMemsetAsync(d_bucket_cnt.p, 0, (size_t)(n_vo + spg_owners) * SPG_CNT_STRIDE * 8, stream));
+            auto make_args = [&]() {
+                SpgGenArgs g{};
+                g.s.n_rows = rows; g.s.n_owners = spg_owners;
+                g.s.tkeys = d_keys.as<long long>(); g.s.cap = cap; g.s.counters = d_counters.as<long long>(); g.s.group_limit = (long long)(cap / 2);
+                g.s.retry_ctr = d_counters.as<long long>() + 1; g.s.retry = d_retry2[0].as<unsigned long long>();
+                g.s.bucket = d_bucket.as<longlong2>(); g.s.bucket_cnt = d_bucket_cnt.as<unsigned long long>(); g.s.bucket_cap = bucket_cap;
+                g.s.ns = spgg_ns[mm]; g.s.n_pass = passes;
+                g.nbucket = v_nullable ? d_nbucket.as<long long>() : nullptr; g.n_vo = n_vo;
+                g.kdata = (const char*)data[0] + r0 * ks; g.kvalid = valid[0] ? valid[0] + r0 / 8 : nullptr;
+                g.vdata = gs.vcol >= 0 ? (const char*)data[gs.vcol] + r0 * vs : nullptr;
+                g.vvalid = (gs.vcol >= 0 && valid[gs.vcol]) ? valid[gs.vcol] + r0 / 8 : nullptr;
+                g.k_signed = ctype_is_signed_int(kct) ? 1 : 0; g.v_signed = ctype_is_signed_int(vct) ? 1 : 0;
+                g.dropna = dropna ? 1 : 0;
+                g.fl.n = n_funcs;
+                for (int j = 0; j < n_funcs; j++) {
+                    g.fl.kind[j] = funcs[j].kind; g.fl.a0[j] = d_a0[j].as<unsigned long long>();
+                    g.fl.a1[j] = funcs[j].has_a1 ? d_a1[j].as<unsigned long long>() : nullptr;
+                }
+                return g;
+            };
+            SpgGenArgs g = make_args();
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (profiling) { B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1)); B200_CUDA(cudaEventRecord(ev0, stream)); }
+            const int g1 = (int)std::min<int64_t>((int64_t)sms * SPG_TCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
+            const size_t psm = GEN_K1_SMEM;
+            if (ks == 8 && vs == 8) spgg_partition_kernel<8, 8><<<g1, SPG_TTHREADS, psm, stream>>>(g);
+            else if (ks == 8 && vs == 4) spgg_partition_kernel<8, 4><<<g1, SPG_TTHREADS, psm, stream>>>(g);
+            else if (ks == 8) spgg_partition_kernel<8, 0><<<g1, SPG_TTHREADS, psm, stream>>>(g);
+            else if (vs == 8) spgg_partition_kernel<4, 8><<<g1, SPG_TTHREADS, psm, stream>>>(g);
+            else if (vs == 4) spgg_partition_kernel<4, 4><<<g1, SPG_TTHREADS, psm, stream>>>(g);
+            else spgg_partition_kernel<4, 0><<<g1, SPG_TTHREADS, psm, stream>>>(g);
+#define B200_SPGG_K2(S, M, N) spgg_aggregate_kernel<S, M, N><<<spg_owners, SPG_THREADS, spgg_smem[mm], stream>>>(g)
+            switch ((gs.has_sum ? 1 : 0) + (gs.has_mm ? 2 : 0) + (gs.has_nn ? 4 : 0)) {
+                case 0: B200_SPGG_K2(false, false, false); break;
+                case 1: B200_SPGG_K2(true, false, false); break;
+                case 2: B200_SPGG_K2(false, true, false); break;
+                case 3: B200_SPGG_K2(true, true, false); break;
+                case 4: B200_SPGG_K2(false, false, true); break;
+                case 5: B200_SPGG_K2(true, false, true); break;
+                case 6: B200_SPGG_K2(false, true, true); break;
+                default: B200_SPGG_K2(true, true, true); break;
+            }
+#undef B200_SPGG_K2
+            B200_CUDA(cudaGetLastError());
+            if (ev0) { B200_CUDA(cudaEventRecord(ev1, stream)); prof_events.emplace_back(ev0, ev1); }
+            launches += 2; consume_launches++; spg_launches++; spgg_launches++;
+            rows_consumed += rows;
+            read_counters();
+            while (h_counters[1] > 0) {  // partials that found the global table at its limit: grow, replay them
+                const int64_t nr = h_counters[1];
+                spg_retry_rows += nr;
+                uint64_t nc = cap;
+                while (nc < 2ull * (uint64_t)(n_groups + nr)) nc <<= 1;
+                if (nc == cap) nc <<= 1;
+                grow(nc);
+                d_retry2[1].ensure(device, (size_t)nr * GEN_RETRY_WORDS * 8);
+                B200_CUDA(cudaMemcpyAsync(d_retry2[1].p, d_retry2[0].p, (size_t)nr * GEN_RETRY_WORDS * 8, cudaMemcpyDeviceToDevice, stream));
+                B200_CUDA(cudaMemsetAsync((char*)d_counters.p + 8, 0, 8, stream));
+                SpgGenArgs g2 = make_args();
+                spgg_replay_kernel<<<grid_for(nr), 256, 0, stream>>>(g2, d_retry2[1].as<unsigned long long>(), (long long)nr);
+                launches++;
+                B200_CUDA(cudaGetLastError());
+                read_counters();
+            }
+        }
+        n_groups_bound = n_groups;
+    }
+
     // Consume rows [0, n) of device-resident columns.
     void consume_device_chunk(const std::vector<const void*>& data, const std::vector<const uint8_t*>& valid, int64_t n) {
         if (n == 0) return;
@@ -2256,6 +2401,33 @@ class GroupbyState {
             if (force || spg_pass_count(est) > 0) {
                 spg_passes = std::max(1, spg_pass_count(est));
                 consume_spg((const long long*)data[0], vcol >= 0 ? (const long long*)data[vcol] : nullptr, n, sum_j, cnt_j, est > 0 && lc_pick(est), est);
+                return;
+            }
+        }
+        // generic signatures (nullable / 4-byte keys or values / mean / min / max over one integer column): same two-kernel path
+        if (!fast && n >= (1 << 20) && spg_probe() && spgg_enabled) {
+            GenSig gs;
+            if (gen_signature(data, valid, gs)) {
+                int64_t est = std::max(expected_groups_hint, n_groups);
+                std::vector<const void*> d2(data); std::vector<const uint8_t*> v2(valid);
+                int64_t left = n;
+                if (est == 0 && rows_consumed == 0) {  // cardinality unknown: learn it from a prefix through the direct kernel
+                    const int64_t prefix = std::min<int64_t>(n, 1 << 20);
+                    consume_direct(data, valid, prefix, false, -1, -1, -1, /*force_count=*/true);
+                    est = n_groups;
+                    if (prefix == n) return;
+                    for (int c = 0; c < n_cols; c++) {
+                        if (data[c]) d2[c] = (const char*)data[c] + prefix * ctype_size(c_types[c]);
+                        if (valid[c]) v2[c] = valid[c] + prefix / 8;
+                    }
+                    left = n - prefix;
+                }
+                // below ~1000 groups the owners are unevenly loaded (and there is no low-cardinality generic kernel): direct path
+                if (est > LC_SLOTS_BIG / 4 && spgg_pass_count(est, gs.layout) > 0 && left >= (1 << 16)) {
+                    consume_spg_gen(d2, v2, left, gs, spgg_pass_count(est, gs.layout));
+                    return;
+                }
+                consume_direct(d2, v2, left, false, -1, -1, -1, false);
                 return;
             }
         }
@@ -2816,6 +2988,7 @@ int64_t b200_groupby_get_metric(void* state, int32_t which) {
         case 9: return s->spg_retry_rows;
         case 10: return s->lc_launches;
         case 11: return s->co_batches;
+        case 12: return s->spgg_launches;
         case 100: s->profiling = true; return 0;
         default: return -1;
     }

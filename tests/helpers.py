@@ -98,6 +98,11 @@ def assert_frames_equal(got: pd.DataFrame, exp: pd.DataFrame, rtol=1e-5, atol=1e
     assert len(got) == len(exp), (len(got), len(exp))
     g, e = sort_frame(got), sort_frame(exp)
     for c in g.columns:
+        if g[c].dtype.kind in "iu" and e[c].dtype.kind in "iu" and (g[c].isna().any() or e[c].isna().any()):
+            # nullable integer columns: same NA positions, the other values bit-exact
+            np.testing.assert_array_equal(g[c].isna().to_numpy(), e[c].isna().to_numpy(), err_msg=f"column {c} (NA mask)")
+            np.testing.assert_array_equal(g[c].fillna(0).to_numpy(dtype=np.int64), e[c].fillna(0).to_numpy(dtype=np.int64), err_msg=f"column {c}")
+            continue
         gv = g[c].to_numpy(dtype="float64", na_value=np.nan) if g[c].dtype.kind not in "iu" or g[c].isna().any() else g[c].to_numpy()
         ev = e[c].to_numpy(dtype="float64", na_value=np.nan) if e[c].dtype.kind not in "iu" or e[c].isna().any() else e[c].to_numpy()
         if gv.dtype.kind in "iu" and ev.dtype.kind in "iu":

@@ -377,3 +377,84 @@ def test_streaming_batches_are_coalesced_into_fast_path_launches(gpu_lib, oracle
     delete_groupby_state(st)
     assert coalesced >= 90 and fast_launches >= 1, (coalesced, fast_launches)
     assert_frames_equal(positional(got), oracle_groupby_frame(oracle, t, 0, ["sum", "count"], [1, 1]))
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("key_dtype,val_dtype", [("Int64", "Int64"), ("Int32", "Int32"), ("int32", "int64"), ("int64", "Int32")])
+@pytest.mark.parametrize("funcs", [("mean", "min", "max"), ("sum", "count", "size"), ("min",), ("size", "mean", "sum", "count", "max")])
+@pytest.mark.parametrize("dropna", [True, False])
+def test_generic_sm_partitioned_path_nullable_int32_mean_min_max(gpu_lib, oracle, key_dtype, val_dtype, funcs, dropna):
+    """SPG-G (spgg.cuh): >= 2^20-row device batches with nullable / 4-byte keys and values and mean / min / max take the
+    SM-partitioned kernels too (metric 12).  Integer results bit-exact against pandas, mean within rtol 1e-5
+    (bodo/tests/utils.py:179-180).  Covers NA keys (dropped or grouped), NA values (the group must still exist, count for
+    size only), values whose sum needs the high word, and a hint-less state that overflows the global table (retry list)."""
+    from bodo_b200.streaming.groupby import (delete_groupby_state, get_metric, groupby_build_consume_batch,
+                                             groupby_produce_output_batch, init_groupby_state)
+    from tests.helpers import table_to_device
+    rng = np.random.default_rng(7)
+    n, n_groups = 2_400_003, 60_000
+    k = rng.integers(-n_groups // 2, n_groups // 2, n)
+    big = val_dtype.lower() == "int64"
+    v = rng.integers(-(1 << 40) if big else -(1 << 31), (1 << 40) if big else (1 << 31) - 1, n)
+    ks = pd.Series(k).astype(key_dtype.lower())
+    vs = pd.Series(v).astype(val_dtype.lower())
+    if key_dtype[0] == "I":
+        ks = ks.astype(key_dtype).mask(rng.random(n) < 0.03)
+    if val_dtype[0] == "I":
+        vs = vs.astype(val_dtype).mask(rng.random(n) < 0.10)
+        # one group whose values are all NA: must exist, with NA aggregates and size > 0
+        vs = vs.mask(ks == 17)
+    df = pd.DataFrame({"k": ks, "v": vs})
+    t = Table.from_pandas(df)
+    nf = len(funcs)
+    offs, cols, c = [0], [], 0
+    for f in funcs:
+        if f != "size":
+            cols.append(1); c += 1
+        offs.append(c)
+    st = init_groupby_state(-1, (0,), funcs, tuple(offs), tuple(cols), expected_groups=0, output_batch_size=1 << 30, dropna=dropna)
+    groupby_build_consume_batch(st, table_to_device(t), True, True)
+    used = get_metric(st, 12)
+    out, _ = groupby_produce_output_batch(st, True)
+    got = out.to_pandas()
+    delete_groupby_state(st)
+    g = df.groupby("k", as_index=False, dropna=dropna)
+    exp = g.size()[["k"]]
+    for j, f in enumerate(funcs):
+        col = g.size()["size"] if f == "size" else g.agg(x=("v", f))["x"]
+        exp[f"o{j}"] = col.values
+    assert used >= 1, "the generic SM-partitioned kernels were expected to run for this shape"
+    assert_frames_equal(positional(got), positional(exp))
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("n_groups,nullable", [(1_200_000, False), (1_200_000, True), (2_400_000, True)])
+def test_generic_sm_partitioned_path_multi_pass(gpu_lib, n_groups, nullable):
+    """More groups than the owners' shared tables hold at once (min / max slots are 32 B): K2g runs several passes.  With
+    2 passes K1g partitions into owners x passes buckets (each row read once); with more, every pass scans the owner's
+    bucket and tests the rows' pass (the class table of K1g has no room for owners x passes + owners buckets)."""
+    from bodo_b200.streaming.groupby import (delete_groupby_state, get_metric, groupby_build_consume_batch,
+                                             groupby_produce_output_batch, init_groupby_state)
+    from tests.helpers import table_to_device
+    rng = np.random.default_rng(11)
+    n = 4_200_001
+    k = rng.integers(0, n_groups, n)
+    v = rng.integers(-(1 << 45), 1 << 45, n)
+    ks, vs = pd.Series(k), pd.Series(v)
+    if nullable:
+        ks = ks.astype("Int64").mask(rng.random(n) < 0.02)
+        vs = vs.astype("Int64").mask(rng.random(n) < 0.15)
+    df = pd.DataFrame({"k": ks, "v": vs})
+    funcs = ("size", "sum", "min", "max", "mean", "count")
+    st = init_groupby_state(-1, (0,), funcs, (0, 0, 1, 2, 3, 4, 5), (1, 1, 1, 1, 1), expected_groups=n_groups, output_batch_size=1 << 30)
+    groupby_build_consume_batch(st, table_to_device(Table.from_pandas(df)), True, True)
+    used = get_metric(st, 12)
+    out, _ = groupby_produce_output_batch(st, True)
+    got = out.to_pandas()
+    delete_groupby_state(st)
+    g = df.groupby("k", as_index=False)
+    exp = g.size()[["k"]]
+    for j, f in enumerate(funcs):
+        exp[f"o{j}"] = (g.size()["size"] if f == "size" else g.agg(x=("v", f))["x"]).values
+    assert used >= 1
+    assert_frames_equal(positional(got), positional(exp))
