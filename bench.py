@@ -55,7 +55,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000_000)
     ap.add_argument("--ref-sample-rows", type=int, default=512_000_000)
     # --workload join: BASELINE.json configs[2] (benchmarks/join_bench.py); the default workload is the contract's configs[1] / [3]
-    ap.add_argument("--workload", default="groupby", choices=["groupby", "join"])
+    ap.add_argument("--workload", default="groupby", choices=["groupby", "join", "shuffle"])
+    ap.add_argument("--n-dest", type=int, default=8, help="shuffle workload at N=1: destinations to partition into")
     ap.add_argument("--aggs", default="sum,count", help="groupby aggregate functions; anything but sum,count runs the variant bench")
     ap.add_argument("--nullable", action="store_true", help="groupby variant: nullable key (1 %% NA) and value (10 %% NA) columns")
     ap.add_argument("--key-dtype", default="int64", choices=["int64", "int32"])
@@ -206,6 +207,11 @@ def main():
         from benchmarks import join_bench
 
         join_bench.run(args, ClockSampler, peaks)
+        return
+    if args.workload == "shuffle":
+        from benchmarks import shuffle_bench
+
+        shuffle_bench.run(args, ClockSampler, peaks)
         return
     if args.impl == "reference":
         reference_arm(args)

@@ -52,24 +52,29 @@ __global__ void __launch_bounds__(PART_THREADS) dest_hist_kernel(const __grid_co
     for (int d = threadIdx.x; d < n_pes; d += blockDim.x) hist[(size_t)blockIdx.x * n_pes + d] = sh[d];
 }
 
-// K2: one CTA. offsets[cta][d] = sum_{d' < d} total[d'] + sum_{cta' < cta} hist[cta'][d]; totals[d] = rows per dest.
-__global__ void scan_hist_kernel(const unsigned int* hist, int n_ctas, int n_pes, long long* offsets, long long* totals) {
+// K2: one CTA of 1024 threads. offsets[cta][d] = sum_{d' < d} total[d'] + sum_{cta' < cta} hist[cta'][d]; totals[d] = rows per dest.
+// Warp w scans the CTA axis of destinations w, w + 32, ... with shuffles (the histogram has n_ctas x n_pes entries, ~10^4).
+__global__ void __launch_bounds__(1024) scan_hist_kernel(const unsigned int* hist, int n_ctas, int n_pes, long long* offsets, long long* totals) {
     __shared__ long long tot[MAX_PES];
-    for (int d = threadIdx.x; d < n_pes; d += blockDim.x) {
-        long long s = 0;
-        for (int c = 0; c < n_ctas; c++) s += hist[(size_t)c * n_pes + d];
-        tot[d] = s;
-        totals[d] = s;
+    __shared__ long long base[MAX_PES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = warp; d < n_pes; d += 32) {
+        long long carry = 0;
+        for (int c0 = 0; c0 < n_ctas; c0 += 32) {
+            const int c = c0 + lane;
+            const long long x = c < n_ctas ? (long long)hist[(size_t)c * n_pes + d] : 0;
+            long long inc = x;
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) { long long y = __shfl_up_sync(0xffffffffu, inc, k); if (lane >= k) inc += y; }
+            if (c < n_ctas) offsets[(size_t)c * n_pes + d] = carry + inc - x;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) { tot[d] = carry; totals[d] = carry; }
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < n_pes; d += blockDim.x) {
-        long long base = 0;
-        for (int e = 0; e < d; e++) base += tot[e];
-        for (int c = 0; c < n_ctas; c++) {
-            offsets[(size_t)c * n_pes + d] = base;
-            base += hist[(size_t)c * n_pes + d];
-        }
-    }
+    if (threadIdx.x == 0) { long long b = 0; for (int d = 0; d < n_pes; d++) { base[d] = b; b += tot[d]; } }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_ctas * n_pes; j += blockDim.x) offsets[j] += base[j % n_pes];
 }
 
 struct ScatterArgs {
@@ -87,50 +92,139 @@ struct ScatterArgs {
     long long* perm_out;  // optional: source row of every output row (tests), may be nullptr
 };
 
-// K3: stable multi-split. Per 256-row chunk: rank inside the warp via __match_any_sync, across warps via a
-// [warps][n_pes] count matrix in shared memory.
+// K3: stable multi-split.  A CTA walks its tile in chunks of PART_THREADS * SC_STEPS rows; inside a chunk every warp owns a
+// contiguous block of 32 * SC_STEPS rows and ranks them in row order with one MATCH.ANY per 32 rows (rank inside the step +
+// rows of that destination the warp saw in earlier steps, kept in the warp's row of wtot); the warps' totals are combined once
+// per chunk, so a chunk costs four CTA barriers for 2048 rows.
+constexpr int SC_STEPS = 8;
 __global__ void __launch_bounds__(PART_THREADS) scatter_kernel(const __grid_constant__ ScatterArgs a) {
     constexpr int NW = PART_THREADS / 32;
-    __shared__ long long run[MAX_PES];        // next output row per destination for this CTA
-    __shared__ unsigned int wcnt[NW][MAX_PES];  // rows of dest d in warp w of the current chunk
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int d = threadIdx.x; d < a.n_pes; d += blockDim.x) run[d] = a.offsets[(size_t)blockIdx.x * a.n_pes + d];
-    int64_t r0 = (int64_t)blockIdx.x * a.tile_rows;
-    int64_t r1 = r0 + a.tile_rows < a.n ? r0 + a.tile_rows : a.n;
-    for (int64_t c0 = r0; c0 < r1; c0 += PART_THREADS) {
-        for (int j = threadIdx.x; j < NW * MAX_PES; j += blockDim.x) (&wcnt[0][0])[j] = 0;
+    __shared__ long long run[MAX_PES];          // next output row per destination for this CTA
+    __shared__ unsigned int wtot[NW * MAX_PES];  // [warp][n_pes] rows of destination d in the warp's block of the current chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, P = a.n_pes;
+    for (int d = threadIdx.x; d < P; d += blockDim.x) run[d] = a.offsets[(size_t)blockIdx.x * P + d];
+    const int64_t r0 = (int64_t)blockIdx.x * a.tile_rows;
+    const int64_t r1 = r0 + a.tile_rows < a.n ? r0 + a.tile_rows : a.n;
+    for (int64_t c0 = r0; c0 < r1; c0 += PART_THREADS * SC_STEPS) {
+        for (int j = threadIdx.x; j < NW * P; j += blockDim.x) wtot[j] = 0;
         __syncthreads();
-        int64_t i = c0 + threadIdx.x;
-        bool in = i < r1;
-        int d = in ? (int)a.dest8[i] : -1;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        int rank_in_warp = __popc(peers & ((1u << lane) - 1));
-        if (in && rank_in_warp == 0) wcnt[warp][d] = __popc(peers);
-        __syncthreads();
-        long long pos = 0;
-        if (in) {
-            unsigned before = 0;
-            for (int w = 0; w < warp; w++) before += wcnt[w][d];
-            pos = run[d] + before + rank_in_warp;
+        const int64_t b0 = c0 + (int64_t)warp * 32 * SC_STEPS;
+        int d[SC_STEPS];
+        unsigned int rk[SC_STEPS];
+#pragma unroll
+        for (int s = 0; s < SC_STEPS; s++) {
+            const int64_t i = b0 + s * 32 + lane;
+            const bool in = i < r1;
+            d[s] = in ? (int)a.dest8[i] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, d[s]);
+            const int rank = __popc(peers & ((1u << lane) - 1));
+            const bool leader = in && rank == 0;
+            unsigned int old = leader ? wtot[warp * P + d[s]] : 0u;
+            if (leader) wtot[warp * P + d[s]] = old + (unsigned int)__popc(peers);
+            old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+            rk[s] = old + (unsigned int)rank;
+            __syncwarp();
         }
         __syncthreads();
-        // advance the per-destination cursors by this chunk's totals
-        for (int e = threadIdx.x; e < a.n_pes; e += blockDim.x) {
-            unsigned t = 0;
-            for (int w = 0; w < NW; w++) t += wcnt[w][e];
+        long long pos[SC_STEPS];
+#pragma unroll
+        for (int s = 0; s < SC_STEPS; s++) {
+            pos[s] = 0;
+            if (d[s] < 0) continue;
+            unsigned int before = 0;
+            for (int w = 0; w < warp; w++) before += wtot[w * P + d[s]];
+            pos[s] = run[d[s]] + before + rk[s];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < P; e += blockDim.x) {  // advance the per-destination cursors by this chunk's totals
+            unsigned int t = 0;
+            for (int w = 0; w < NW; w++) t += wtot[w * P + e];
             run[e] += t;
         }
-        if (in) {
-            if (a.perm_out) a.perm_out[pos] = i;
+#pragma unroll
+        for (int s = 0; s < SC_STEPS; s++) {
+            if (d[s] < 0) continue;
+            const int64_t i = b0 + s * 32 + lane;
+            const long long p = pos[s];
+            if (a.perm_out) a.perm_out[p] = i;
             for (int c = 0; c < a.n_cols; c++) {
                 switch (a.itemsize[c]) {
-                    case 8: ((uint64_t*)a.out_data[c])[pos] = ((const uint64_t*)a.in_data[c])[i]; break;
-                    case 4: ((uint32_t*)a.out_data[c])[pos] = ((const uint32_t*)a.in_data[c])[i]; break;
-                    case 2: ((uint16_t*)a.out_data[c])[pos] = ((const uint16_t*)a.in_data[c])[i]; break;
-                    default: ((uint8_t*)a.out_data[c])[pos] = ((const uint8_t*)a.in_data[c])[i]; break;
+                    case 8: ((uint64_t*)a.out_data[c])[p] = __ldcs((const unsigned long long*)a.in_data[c] + i); break;
+                    case 4: ((uint32_t*)a.out_data[c])[p] = __ldcs((const unsigned int*)a.in_data[c] + i); break;
+                    case 2: ((uint16_t*)a.out_data[c])[p] = ((const uint16_t*)a.in_data[c])[i]; break;
+                    default: ((uint8_t*)a.out_data[c])[p] = ((const uint8_t*)a.in_data[c])[i]; break;
                 }
-                if (a.out_valid_bytes[c]) a.out_valid_bytes[c][pos] = bit_valid(a.in_valid[c], i) ? 1 : 0;
+                if (a.out_valid_bytes[c]) a.out_valid_bytes[c][p] = bit_valid(a.in_valid[c], i) ? 1 : 0;
             }
+        }
+        __syncthreads();
+    }
+}
+
+// K3, specialised: at most 8 destinations (one NVLink box), NC 8-byte columns without validity bitmaps.  Same row order as
+// scatter_kernel, but the stable rank comes from eight ballots per 32 rows and the warp's running per-destination counts live
+// in registers (16-bit fields of two 64-bit words, identical in every lane): no shared-memory traffic and no warp barrier in
+// the ranking loop, one 16-byte shared store per warp and three CTA barriers per 2048-row chunk.
+template <int NC>
+__global__ void __launch_bounds__(PART_THREADS) scatter_small_kernel(const __grid_constant__ ScatterArgs a) {
+    constexpr int NW = PART_THREADS / 32;
+    __shared__ long long run[8];
+    __shared__ unsigned long long wtot[NW][2];  // per warp: rows per destination of its block, 16-bit fields
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, P = a.n_pes;
+    if (threadIdx.x < 8) run[threadIdx.x] = threadIdx.x < P ? a.offsets[(size_t)blockIdx.x * P + threadIdx.x] : 0;
+    const int64_t r0 = (int64_t)blockIdx.x * a.tile_rows;
+    const int64_t r1 = r0 + a.tile_rows < a.n ? r0 + a.tile_rows : a.n;
+    const unsigned lt = (1u << lane) - 1;
+    for (int64_t c0 = r0; c0 < r1; c0 += PART_THREADS * SC_STEPS) {
+        const int64_t b0 = c0 + (int64_t)warp * 32 * SC_STEPS;
+        int d[SC_STEPS];
+        unsigned long long v[NC][SC_STEPS];
+#pragma unroll
+        for (int s = 0; s < SC_STEPS; s++) {  // all loads of the chunk are issued before anything depends on them
+            const int64_t i = b0 + s * 32 + lane;
+            d[s] = i < r1 ? (int)a.dest8[i] : 8;
+#pragma unroll
+            for (int c = 0; c < NC; c++) v[c][s] = i < r1 ? __ldcs((const unsigned long long*)a.in_data[c] + i) : 0ull;
+        }
+        unsigned long long cl = 0, ch = 0;  // rows per destination this warp has ranked so far (dests 0-3 / 4-7)
+        unsigned int rk[SC_STEPS];
+#pragma unroll
+        for (int s = 0; s < SC_STEPS; s++) {
+            unsigned int mine = 0;
+            unsigned long long al = 0, ah = 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const unsigned b = __ballot_sync(0xffffffffu, d[s] == e);
+                if (d[s] == e) mine = (unsigned int)__popc(b & lt);
+                if (e < 4) al += (unsigned long long)__popc(b) << (16 * e);
+                else ah += (unsigned long long)__popc(b) << (16 * (e - 4));
+            }
+            const unsigned long long w = (d[s] & 4) ? ch : cl;
+            rk[s] = mine + (unsigned int)((w >> (16 * (d[s] & 3))) & 0xffffu);
+            cl += al; ch += ah;
+        }
+        if (lane == 0) { wtot[warp][0] = cl; wtot[warp][1] = ch; }
+        __syncthreads();
+        unsigned long long bl = 0, bh = 0;  // rows of the warps before this one
+        for (int w = 0; w < warp; w++) { bl += wtot[w][0]; bh += wtot[w][1]; }
+        long long pos[SC_STEPS];
+#pragma unroll
+        for (int s = 0; s < SC_STEPS; s++) {
+            const unsigned long long w = (d[s] & 4) ? bh : bl;
+            pos[s] = d[s] < 8 ? run[d[s]] + (long long)((w >> (16 * (d[s] & 3))) & 0xffffu) + rk[s] : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            unsigned long long t = 0;
+            for (int w = 0; w < NW; w++) t += (wtot[w][threadIdx.x >> 2] >> (16 * (threadIdx.x & 3))) & 0xffffull;
+            run[threadIdx.x] += (long long)t;
+        }
+#pragma unroll
+        for (int s = 0; s < SC_STEPS; s++) {
+            if (d[s] >= 8) continue;
+            if (a.perm_out) a.perm_out[pos[s]] = b0 + s * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < NC; c++) ((unsigned long long*)a.out_data[c])[pos[s]] = v[c][s];
         }
         __syncthreads();
     }
@@ -219,12 +313,13 @@ void shuffle_partition(const b200_table* in, int64_t n_keys, int n_pes, b200_tab
     if (n == 0) return;
     int sms = num_sms(dev);
     int n_ctas = (int)std::min<int64_t>((int64_t)sms * 8, (n + PART_THREADS - 1) / PART_THREADS);
-    int64_t tile_rows = ((n + n_ctas - 1) / n_ctas + PART_THREADS - 1) / PART_THREADS * PART_THREADS;
+    const int64_t chunk = (int64_t)PART_THREADS * SC_STEPS;
+    int64_t tile_rows = ((n + n_ctas - 1) / n_ctas + chunk - 1) / chunk * chunk;
     n_ctas = (int)((n + tile_rows - 1) / tile_rows);
     StreamBuf dest8((size_t)n, st), hist((size_t)n_ctas * n_pes * 4, st), offsets((size_t)n_ctas * n_pes * 8, st), totals((size_t)n_pes * 8, st);
     dest_hist_kernel<<<n_ctas, PART_THREADS, 0, st>>>(ks, n, tile_rows, n_pes, dest8.as<uint8_t>(), hist.as<unsigned int>());
     B200_CUDA(cudaGetLastError());
-    scan_hist_kernel<<<1, 256, 0, st>>>(hist.as<unsigned int>(), n_ctas, n_pes, offsets.as<long long>(), totals.as<long long>());
+    scan_hist_kernel<<<1, 1024, 0, st>>>(hist.as<unsigned int>(), n_ctas, n_pes, offsets.as<long long>(), totals.as<long long>());
     B200_CUDA(cudaGetLastError());
     ScatterArgs a{};
     a.n = n; a.tile_rows = tile_rows; a.n_pes = n_pes; a.n_cols = in->n_cols; a.dest8 = dest8.as<uint8_t>();
@@ -244,7 +339,18 @@ void shuffle_partition(const b200_table* in, int64_t n_keys, int n_pes, b200_tab
         }
         oc.length = n; oc.c_type = ic.c_type; oc.arr_type = ic.arr_type;
     }
-    scatter_kernel<<<n_ctas, PART_THREADS, 0, st>>>(a);
+    bool small = n_pes <= 8 && in->n_cols <= 4;
+    for (int c = 0; c < in->n_cols; c++) small = small && a.itemsize[c] == 8 && !a.in_valid[c];
+    if (small) {
+        switch (in->n_cols) {
+            case 1: scatter_small_kernel<1><<<n_ctas, PART_THREADS, 0, st>>>(a); break;
+            case 2: scatter_small_kernel<2><<<n_ctas, PART_THREADS, 0, st>>>(a); break;
+            case 3: scatter_small_kernel<3><<<n_ctas, PART_THREADS, 0, st>>>(a); break;
+            default: scatter_small_kernel<4><<<n_ctas, PART_THREADS, 0, st>>>(a); break;
+        }
+    } else {
+        scatter_kernel<<<n_ctas, PART_THREADS, 0, st>>>(a);
+    }
     B200_CUDA(cudaGetLastError());
     for (int c = 0; c < in->n_cols; c++) {
         if (!vbytes[c]) continue;
