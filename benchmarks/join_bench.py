@@ -6,7 +6,8 @@ every batch materialising its joined rows (kept columns: k, b1, b2 of the build 
 
   value     probe rows/s with both inputs resident in HBM (CUDA events around the step)
   e2e       the same through the same API with HOST (pinned) inputs and every output batch copied back to pinned host memory
-  roofline  dominant kernel join_probe_fast_kernel: (24 B probe row + 40 B output row) x rows of a launch / its launch time
+  roofline  dominant kernel join_probe_inline_kernel (Slot32 table: key + payload in one sector; join_probe_fast_kernel when the
+            schema does not qualify): (24 B probe row + 40 B output row) x rows of a launch / its launch time
             (CUDA events on the operator's stream), against MEASURED_PEAKS.json hbm_gbs; the random slot + payload sectors a
             probe touches (>= 64 B/row) are NOT in the algorithmic figure
   parity    untimed, at full size: row count; sum mod 2^64 of EVERY output column against an independent torch computation
@@ -134,6 +135,7 @@ def run(args, ClockSampler, peaks):
                 sample_rows.append(torch.stack([c.view(torch.int64)[m] for c in cols], 1).cpu())
         stats["launches"] = J.get_metric(st, 4)
         stats["fast_probes"] = J.get_metric(st, 5)
+        stats["inline_probes"] = J.get_metric(st, 6)
         J.delete_join_state(st)
         if profile:
             torch.cuda.synchronize(dev)
@@ -187,7 +189,7 @@ def run(args, ClockSampler, peaks):
     achieved = sum(alg_bytes) / 1e9 / (sum(pms) * 1e-3)
     stream_gb = (nb * 24 + npr * 24 + out_rows * 40) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
-                "kernel": "join_probe_fast_kernel (one launch per probe batch)", "launches_per_step": len(pms), "avg_launch_ms": sum(pms) / len(pms),
+                "kernel": ("join_probe_inline_kernel<2,2>" if stats.get("inline_probes") else "join_probe_fast_kernel") + " (one launch per probe batch)", "launches_per_step": len(pms), "avg_launch_ms": sum(pms) / len(pms),
                 "algorithmic_bytes_per_launch": alg_bytes[0], "algorithmic_bytes_per_row": "24 B probe row in + 40 B joined row out",
                 "compulsory_stream_gb_per_step": stream_gb, "whole_step_frac": stream_gb / (ms / args.steps * 1e-3) / peak}
 

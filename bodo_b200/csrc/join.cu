@@ -422,6 +422,160 @@ __global__ void __launch_bounds__(256) join_probe_fast_kernel(const __grid_const
     }
 }
 
+// ---- inline-payload probe: the specialisation for all-8-byte, bitmap-free schemas with at most two build payload columns ----
+// Slot32 = {key, f0, f1, first | cnt << 32}: key AND payload of a unique-key build row sit in ONE 32-byte sector, so a probe
+// row costs one random sector instead of two (Slot16 + packed payload row).  All coalesced loads of a tile (key and the kept
+// probe columns, 4 rows per thread) are issued before the first dependent table access.
+struct __align__(32) Slot32 { long long key; unsigned long long f0, f1; uint32_t first; uint32_t cnt; };
+constexpr int J_INL_MAX_P = 4;
+struct InlineProbeArgs {
+    int64_t n_probe;
+    const long long* key;
+    const Slot32* slots; uint64_t cap;
+    unsigned long long* cursor;
+    int n_b;                       // kept build columns (<= 3)
+    int b_field[4];                // -1 = key, 0 / 1 = payload field
+    unsigned long long* ob[4];
+    const unsigned long long* p[J_INL_MAX_P];  // kept probe columns (the key column included when kept)
+    unsigned long long* op[J_INL_MAX_P];
+};
+// Direct build of the Slot32 table (no separate key table / slot-info / CSR passes): one random 32-byte sector per build row.
+// A row claims its slot with a CAS on the key word, counts itself in the slot and, when it is the first row of that key,
+// writes the payload.  A second row of any key raises *dup: the host then falls back to the general build (CSR groups).
+__global__ void join_fill_slots32_kernel(Slot32* slots, uint64_t n_slots) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const ulonglong4 e = make_ulonglong4((unsigned long long)J_EMPTY, 0ull, 0ull, 0ull);
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += stride) reinterpret_cast<ulonglong4*>(slots)[s] = e;
+}
+__global__ void __launch_bounds__(256) join_build_inline_kernel(const long long* __restrict__ keys, const unsigned long long* __restrict__ f0, const unsigned long long* __restrict__ f1,
+                                                                int64_t n, int64_t row0, Slot32* slots, uint64_t cap, int* dup) {
+    constexpr int R = 4;
+    const uint64_t mask = cap - 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * R;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x * R + threadIdx.x; i0 < n; i0 += stride) {
+        long long key[R], k0[R];
+        uint64_t s[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) { const int64_t i = i0 + r * 256; key[r] = i < n ? __ldcs(keys + i) : 0; }
+#pragma unroll
+        for (int r = 0; r < R; r++) {  // the R first probes are in flight together
+            s[r] = key[r] == J_EMPTY ? cap + 1 : j_hash_slot(key[r], mask);
+            k0[r] = __ldcg(&slots[s[r]].key);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int64_t i = i0 + r * 256;
+            if (i >= n) continue;
+            bool won = false;  // this row claimed a free slot (it is the first row of its key)
+            if (key[r] != J_EMPTY) {
+                long long k = k0[r];
+                while (true) {
+                    if (k == J_EMPTY) {
+                        const long long prev = (long long)atomicCAS((unsigned long long*)&slots[s[r]].key, (unsigned long long)J_EMPTY, (unsigned long long)key[r]);
+                        if (prev == J_EMPTY) { won = true; break; }
+                        k = prev;
+                    }
+                    if (k == key[r]) break;  // another row holds this key: duplicate
+                    s[r] = (s[r] + 1) & mask;
+                    k = __ldcg(&slots[s[r]].key);
+                }
+            } else {
+                won = atomicAdd(&slots[s[r]].cnt, 1u) == 0;  // marker-key slot: its key word stays the free-slot pattern
+            }
+            if (won) {  // the rest of the sector: f0 (8 B), then {f1, first, cnt = 1} (16 B)
+                slots[s[r]].f0 = f0 ? __ldcs(f0 + i) : 0ull;
+                const unsigned long long f1v = f1 ? __ldcs(f1 + i) : 0ull;
+                *reinterpret_cast<ulonglong2*>(&slots[s[r]].f1) = make_ulonglong2(f1v, (unsigned long long)(uint32_t)(row0 + i) | (1ull << 32));
+            } else *dup = 1;
+        }
+    }
+}
+__global__ void join_slots16_from32_kernel(const Slot32* in, uint64_t n_slots, Slot16* out) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += stride) {
+        Slot16 e; e.key = in[s].key; e.first = in[s].first; e.cnt = in[s].cnt;
+        out[s] = e;
+    }
+}
+template <int NF, int NPK>
+__global__ void __launch_bounds__(256) join_probe_inline_kernel(const __grid_constant__ InlineProbeArgs a) {
+    constexpr int R = 4, NW = 8, TILE = 256 * R;
+    __shared__ unsigned int wcnt[R * NW];
+    __shared__ unsigned int woff[R * NW];
+    __shared__ unsigned long long tile_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t mask = a.cap - 1;
+    const int64_t n_tiles = (a.n_probe + TILE - 1) / TILE;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        long long key[R];
+        unsigned long long pv[NPK][R], f0[R], f1[R];
+        unsigned int rank[R];
+        bool match[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int64_t i = t * TILE + r * 256 + threadIdx.x;
+            const bool in = i < a.n_probe;
+            key[r] = in ? __ldcs(a.key + i) : 0;
+#pragma unroll
+            for (int c = 0; c < NPK; c++) pv[c][r] = in ? __ldcs(a.p[c] + i) : 0ull;
+        }
+        // first probe of all R rows: the R random 256-bit slot loads (one sector, one request each) are in flight together;
+        // a data-dependent probe loop per row would serialise them
+        uint64_t sl[R];
+        unsigned long long w0[R], w1[R], w2[R], w3[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            sl[r] = key[r] == J_EMPTY ? a.cap + 1 : j_hash_slot(key[r], mask);
+            asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(w0[r]), "=l"(w1[r]), "=l"(w2[r]), "=l"(w3[r]) : "l"(a.slots + sl[r]));
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int64_t i = t * TILE + r * 256 + threadIdx.x;
+            match[r] = false; f0[r] = 0; f1[r] = 0;
+            if (i >= a.n_probe) continue;
+            while (true) {
+                if ((long long)w0[r] == key[r]) {
+                    if (NF >= 1) f0[r] = w1[r];
+                    if (NF >= 2) f1[r] = w2[r];
+                    match[r] = (unsigned int)(w3[r] >> 32) > 0;
+                    break;
+                }
+                if ((long long)w0[r] == J_EMPTY || sl[r] > mask) break;  // free slot, or the marker-key slot (cap + 1) without a build row
+                sl[r] = (sl[r] + 1) & mask;  // collision (about one row in four at this load factor): next slot
+                asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(w0[r]), "=l"(w1[r]), "=l"(w2[r]), "=l"(w3[r]) : "l"(a.slots + sl[r]));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            unsigned m = __ballot_sync(0xffffffffu, match[r]);
+            rank[r] = __popc(m & ((1u << lane) - 1));
+            if (lane == 0) wcnt[r * NW + warp] = __popc(m);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int x = wcnt[lane], inc = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { unsigned int y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
+            woff[lane] = inc - x;
+            if (lane == 31) tile_base = inc ? atomicAdd(a.cursor, (unsigned long long)inc) : 0ull;
+        }
+        __syncthreads();
+        const unsigned long long base = tile_base;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (!match[r]) continue;
+            const int64_t orow = (int64_t)(base + woff[r * NW + warp] + rank[r]);
+            for (int k2 = 0; k2 < a.n_b; k2++) {
+                const int f = a.b_field[k2];
+                a.ob[k2][orow] = f < 0 ? (unsigned long long)key[r] : (f == 0 ? f0[r] : f1[r]);
+            }
+#pragma unroll
+            for (int c = 0; c < NPK; c++) a.op[c][orow] = pv[c][r];
+        }
+        __syncthreads();
+    }
+}
+
 // ================================================================================================
 struct GrowCol {  // growable device column (geometric growth, copy on grow)
     DevBuf buf;
@@ -456,7 +610,9 @@ class JoinState {
     uint64_t cap = 0;
     DevBuf d_tkeys, d_info, d_row_slot, d_cnt_multi, d_goffs, d_groups, d_fill, d_bmatched;
     DevBuf d_slots16, d_bpack, d_cursor;  // fast path (unique build keys, inner join)
-    bool fast_ready = false;
+    DevBuf d_slots32;                      // inline-payload table (all-8-byte bitmap-free build schema, <= 2 payload columns)
+    bool fast_ready = false, inline_ready = false;
+    int64_t inline_probes = 0, inline_builds = 0;
     unsigned long long* h_cursor = nullptr;
     int64_t fast_probes = 0;
     Scanner scan;
@@ -552,10 +708,57 @@ class JoinState {
         if (is_last) finalize_build();
     }
 
+    // Inline-payload build attempt (unique keys expected): true when the Slot32 table is complete, false when a key repeats
+    // (or the schema does not qualify) and the general build has to run.
+    bool try_inline_build(uint64_t n_slots) {
+        const int nf = n_b - 1;
+        bool ok = n_build > 0 && nf <= 2 && !build_outer && !probe_outer && !(getenv("B200_JOIN_INLINE") && getenv("B200_JOIN_INLINE")[0] == '0');
+        for (int c = 0; c < n_b; c++) ok = ok && ctype_size(b_ct[c]) == 8 && !b_has_valid[c];
+        if (!ok) return false;
+        d_slots32.alloc(n_slots * sizeof(Slot32));
+        d_cursor.alloc(8);
+        B200_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, stream));
+        join_fill_slots32_kernel<<<grid_for((int64_t)n_slots), 256, 0, stream>>>(d_slots32.as<Slot32>(), n_slots);
+        join_build_inline_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>((n_build + 1023) / 1024, (int64_t)sms * 8)), 256, 0, stream>>>(bcol[0].buf.as<long long>(), nf > 0 ? bcol[1].buf.as<unsigned long long>() : nullptr,
+                                                                       nf > 1 ? bcol[2].buf.as<unsigned long long>() : nullptr, n_build, 0, d_slots32.as<Slot32>(), cap,
+                                                                       (int*)d_cursor.p);
+        launches += 2;
+        B200_CUDA(cudaGetLastError());
+        if (!h_cursor) h_cursor = (unsigned long long*)pinned_acquire(8);
+        B200_CUDA(cudaMemcpyAsync(h_cursor, d_cursor.p, 8, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA(cudaStreamSynchronize(stream));
+        if (*h_cursor != 0) { d_slots32.release(); return false; }  // duplicate build keys
+        return true;
+    }
+    // Slot16 table + packed payload of the two-sector fast kernel, derived on demand when a probe batch does not qualify for the
+    // inline kernel (bitmaps, narrow columns) after an inline build
+    void ensure_fast_tables() {
+        if (d_slots16.p) return;
+        const uint64_t n_slots = cap + 2;
+        d_slots16.alloc(n_slots * sizeof(Slot16));
+        join_slots16_from32_kernel<<<grid_for((int64_t)n_slots), 256, 0, stream>>>(d_slots32.as<Slot32>(), n_slots, d_slots16.as<Slot16>());
+        const int nf = n_b - 1;
+        d_bpack.alloc((size_t)std::max<int64_t>(n_build * std::max(nf, 1), 1) * 8);
+        if (nf > 0) {
+            PackPayloadArgs pa{};
+            pa.n_build = n_build; pa.n_fields = nf; pa.out = d_bpack.as<unsigned long long>();
+            for (int c = 1; c < n_b; c++) { pa.src[c - 1] = bcol[c].buf.p; pa.size[c - 1] = ctype_size(b_ct[c]); }
+            join_pack_payload_kernel<<<grid_for(n_build), 256, 0, stream>>>(pa);
+        }
+        launches += 2;
+        B200_CUDA(cudaGetLastError());
+    }
+
     void finalize_build() {
         cap = 1024;
         while (cap < 2ull * (uint64_t)n_build) cap <<= 1;
         uint64_t n_slots = cap + 2;
+        if (try_inline_build(n_slots)) {
+            d_goffs.alloc(8); d_groups.alloc(8);
+            fast_ready = true; inline_ready = true; inline_builds++;
+            build_final = true;
+            return;
+        }
         d_tkeys.alloc(n_slots * 8);
         fill_i64_kernel<<<grid_for((int64_t)n_slots), 256, 0, stream>>>(d_tkeys.as<long long>(), n_slots, J_EMPTY);
         d_info.alloc(n_slots * sizeof(SlotInfo));
@@ -592,7 +795,7 @@ class JoinState {
                     join_pack_payload_kernel<<<grid_for(n_build), 256, 0, stream>>>(pa);
                 }
                 d_cursor.alloc(8);
-                h_cursor = (unsigned long long*)pinned_acquire(8);
+                if (!h_cursor) h_cursor = (unsigned long long*)pinned_acquire(8);
                 launches += 2;
                 fast_ready = true;
                 d_tkeys.release(); d_info.release();  // the general-path table is not needed any more
@@ -655,7 +858,29 @@ class JoinState {
                 }
             }
             B200_CUDA(cudaMemsetAsync(d_cursor.p, 0, 8, stream));
-            join_probe_fast_kernel<<<(int)std::min<int64_t>((int64_t)sms * 8, (n + 1023) / 1024), 256, 0, stream>>>(f);
+            // inline-payload variant: every column of this batch 8 bytes wide and bitmap-free, 1..4 kept probe columns
+            bool inl = inline_ready && valid[0] == nullptr && kp.size() >= 1 && kp.size() <= (size_t)J_INL_MAX_P && kb.size() <= 4;
+            for (int src : kp) inl = inl && ctype_size(p_ct[src]) == 8 && valid[src] == nullptr;
+            for (int k = 0; k < n_out_cols; k++) inl = inl && !out_has_valid[k];  // (a nullable-typed column without a bitmap still gets one)
+            const int gridp = (int)std::min<int64_t>((int64_t)sms * 8, (n + 1023) / 1024);
+            if (inl) {
+                InlineProbeArgs ia{};
+                ia.n_probe = n; ia.key = (const long long*)data[0]; ia.slots = d_slots32.as<Slot32>(); ia.cap = cap;
+                ia.cursor = d_cursor.as<unsigned long long>(); ia.n_b = (int)kb.size();
+                for (size_t k = 0; k < kb.size(); k++) { ia.b_field[k] = kb[k] - 1; ia.ob[k] = out_data[k].as<unsigned long long>(); }
+                for (size_t j = 0; j < kp.size(); j++) { ia.p[j] = (const unsigned long long*)data[kp[j]]; ia.op[j] = out_data[kb.size() + j].as<unsigned long long>(); }
+                const int nf = n_b - 1;
+#define B200_INL(NF, NPK) join_probe_inline_kernel<NF, NPK><<<gridp, 256, 0, stream>>>(ia)
+#define B200_INL_NF(NF) do { switch (kp.size()) { case 1: B200_INL(NF, 1); break; case 2: B200_INL(NF, 2); break; case 3: B200_INL(NF, 3); break; default: B200_INL(NF, 4); break; } } while (0)
+                if (nf <= 0) B200_INL_NF(0); else if (nf == 1) B200_INL_NF(1); else B200_INL_NF(2);
+#undef B200_INL_NF
+#undef B200_INL
+                inline_probes++;
+            } else {
+                ensure_fast_tables();
+                f.slots = d_slots16.as<Slot16>(); f.bpack = d_bpack.as<unsigned long long>();
+                join_probe_fast_kernel<<<gridp, 256, 0, stream>>>(f);
+            }
             launches++; fast_probes++;
             B200_CUDA(cudaGetLastError());
             B200_CUDA(cudaMemcpyAsync(h_cursor, d_cursor.p, 8, cudaMemcpyDeviceToHost, stream));
@@ -859,6 +1084,8 @@ int64_t b200_join_get_metric(void* state, int32_t which) {
         case 3: return s->out_rows_total;
         case 4: return s->launches;
         case 5: return s->fast_probes;
+        case 6: return s->inline_probes;
+        case 7: return s->inline_builds;
         default: return -1;
     }
 }

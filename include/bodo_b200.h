@@ -127,7 +127,8 @@ void b200_delete_groupby_state(void* state);
  * 6 accumulated device time of the consume kernel in microseconds (CUDA events on the state's stream;
  * only when profiling was enabled by querying metric 100 first), 7 consume-kernel launches, 8 SM-partitioned
  * (SPG) launches, 9 rows/partials replayed from the SPG retry lists, 10 low-cardinality (LC) launches, 11 small batches
- * that were coalesced on the device before a fast-path launch. */
+ * that were coalesced on the device before a fast-path launch, 12 SPG launches of the generic signature (SPG-G: nullable /
+ * 4-byte keys or values, mean / min / max; included in 8). */
 int64_t b200_groupby_get_metric(void* state, int32_t which);
 
 /* ---- streaming hash join (reference: bodo/libs/streaming/_join.cpp) ---- */
@@ -161,6 +162,9 @@ int b200_join_probe_consume_batch(void* state, const b200_table* in_table,
 
 /* delete_join_state (_join.cpp:4429). */
 void b200_delete_join_state(void* state);
+/* Operator metrics (the reference's JoinMetrics, bodo/libs/streaming/_join.h): 0 build rows, 1 hash-table slots, 2 probe rows,
+ * 3 output rows, 4 kernel launches, 5 probe batches through a fused (unique-build-key) probe kernel, 6 of those through the
+ * inline-payload kernel (key + payload in one 32-byte slot), 7 inline-payload table builds. */
 int64_t b200_join_get_metric(void* state, int32_t which);
 
 /* ---- row -> rank shuffle (reference: bodo/libs/_shuffle.cpp) ---- */

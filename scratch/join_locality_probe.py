@@ -1,0 +1,28 @@
+"""Experiment: how fast is the inline-payload probe when the touched part of the build table is L2 resident?
+probe keys are drawn from the first `hot` build keys (random slots all over the table, `hot` x 32 B of distinct sectors)."""
+import sys, time
+import torch
+sys.path.insert(0, ".")
+from bodo_b200.streaming import join as J
+from bodo_b200.table import Column, Table
+
+dev = torch.device("cuda", 0)
+nb, npr = 100_000_000, 250_000_000
+g = torch.Generator(device=dev); g.manual_seed(1)
+bk = torch.randperm(nb, device=dev, generator=g)
+b1 = torch.arange(nb, device=dev); b2 = torch.rand(nb, device=dev, dtype=torch.float64)
+st = J.init_join_state(-1, (0,), (0,), ("k", "b1", "b2"), ("k", "p1", "p2"), False, False, output_batch_size=1 << 40)
+J.join_build_consume_batch(st, Table([Column(bk), Column(b1), Column(b2)], ["k", "b1", "b2"]), True)
+p1 = torch.arange(npr, device=dev); p2 = torch.rand(npr, device=dev, dtype=torch.float64)
+for hot in (nb, 16_000_000, 4_000_000, 1_000_000, 250_000):
+    idx = torch.randint(0, hot, (npr,), device=dev, generator=g)
+    pk = bk[idx].contiguous()
+    del idx
+    tab = Table([Column(pk), Column(p1), Column(p2)], ["k", "p1", "p2"])
+    for it in range(3):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out, _, _ = J.join_probe_consume_batch(st, tab, False, True, ([0, 1, 2], [1, 2]))
+        e1.record(); torch.cuda.synchronize()
+    print(f"hot keys {hot:>11,}: {e0.elapsed_time(e1):7.2f} ms per {npr:,} probe rows, out rows {out.n_rows:,}, inline probes {J.get_metric(st, 6)}", flush=True)

@@ -142,3 +142,46 @@ def test_na_keys_never_match_on_the_streaming_door(gpu_lib, oracle, build_outer,
     n_inner = 3  # 2-2, 2-2 (probe has two 2s), 3-3
     n_exp = n_inner + (3 if build_outer else 0) + (3 if probe_outer else 0)  # unmatched: build {NA, NA, 7}, probe {NA, 8, NA}
     assert len(got) == n_exp
+
+
+@pytest.mark.parametrize("n_payload", [0, 1, 2])
+def test_inline_payload_probe_matches_oracle(gpu_lib, oracle, n_payload, monkeypatch):
+    """All-8-byte bitmap-free schemas with <= 2 build payload columns probe a Slot32 table (key + payload in one 32-byte
+    sector, join_probe_inline_kernel, metric 6); same rows as the oracle and as the two-sector fast kernel (B200_JOIN_INLINE=0).
+    The marker key (INT64_MIN, the table's free-slot value) is present on both sides."""
+    from bodo_b200.streaming.join import get_metric
+    rng = np.random.default_rng(9)
+    nb, npr = 150_000, 700_001
+    bk = rng.permutation(nb).astype(np.int64) * 3
+    bk[7] = np.iinfo(np.int64).min
+    build = pd.DataFrame({"k": bk})
+    for j in range(n_payload):
+        build[f"b{j}"] = rng.integers(-(1 << 50), 1 << 50, nb) if j == 0 else rng.random(nb)
+    pk = rng.integers(0, nb * 4, npr).astype(np.int64)
+    pk[::1000] = np.iinfo(np.int64).min
+    probe = pd.DataFrame({"k": pk, "p1": rng.integers(0, 1 << 40, npr), "p2": rng.random(npr)})
+    exp = oracle_join_frame(oracle, build, probe)
+
+    def run(used_cols=None):
+        bt, pt = Table.from_pandas(build), Table.from_pandas(probe)
+        st = init_join_state(-1, (0,), (0,), tuple(build.columns), tuple(probe.columns), False, False)
+        join_build_consume_batch(st, table_to_device(bt), True)
+        outs = []
+        for i0 in range(0, npr, 250_000):
+            out, _, _ = join_probe_consume_batch(st, table_to_device(pt.slice(i0, i0 + 250_000)), i0 + 250_000 >= npr, True, used_cols)
+            outs.append(out.to_pandas())
+        m = get_metric(st, 6)
+        delete_join_state(st)
+        return pd.concat(outs, ignore_index=True), m
+
+    got, used = run()
+    assert used >= 1, "the inline-payload probe kernel was expected to run for this schema"
+    assert_rowset_equal(got, exp)
+    nbc = 1 + n_payload
+    got2, used2 = run(([0] if n_payload == 0 else [nbc - 1], [2, 1]))  # kept subset, probe columns reordered
+    assert used2 >= 1
+    assert_rowset_equal(got2, exp.iloc[:, [0 if n_payload == 0 else nbc - 1, nbc + 2, nbc + 1]])
+    monkeypatch.setenv("B200_JOIN_INLINE", "0")
+    got3, used3 = run()
+    assert used3 == 0
+    assert_rowset_equal(got3, exp)
