@@ -171,9 +171,12 @@ __global__ void join_fill_groups_kernel(const uint32_t* row_slot, int64_t n, con
 }
 
 // probe pass A: slot + match count per probe row
+// mode 0: inner / outer join; 1: anti join (a probe row goes out, once and with NULL build columns, iff it has NO match:
+// the is_anti_join template of the reference's probe, _join.cpp:763-767); 2: mark join (every probe row goes out once, without
+// build columns; mark[i] says whether it has a match, _join.cpp:3668-3693)
 __global__ void join_probe_count_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid, int64_t n,
                                         const long long* tkeys, uint64_t cap, const SlotInfo* info, int probe_outer,
-                                        uint32_t* pslot, uint32_t* pcnt, int na_equal) {
+                                        uint32_t* pslot, uint32_t* pcnt, int na_equal, int mode, uint8_t* mark) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t s;
@@ -184,6 +187,8 @@ __global__ void join_probe_count_kernel(const void* key_data, int key_ctype, con
         }
         uint32_t c = s == J_NONE ? 0 : info[s].cnt;
         if (c == 0) s = J_NONE;
+        if (mode == 1) { pslot[i] = J_NONE; pcnt[i] = c ? 0u : 1u; continue; }
+        if (mode == 2) { pslot[i] = J_NONE; pcnt[i] = 1u; mark[i] = c ? 1 : 0; continue; }
         pslot[i] = s;
         pcnt[i] = c ? c : (probe_outer ? 1u : 0u);
     }
@@ -576,6 +581,58 @@ __global__ void __launch_bounds__(256) join_probe_inline_kernel(const __grid_con
     }
 }
 
+// ---- runtime join filter (reference: HashJoinState::RuntimeFilter, bodo/libs/streaming/_join.h:1060-1095; bloom filter
+// bodo/libs/gpu_bloom_filter.cu:60-201; key min / max bodo/libs/streaming/_join.cpp:3199-3238) ----
+// Split-block bloom filter: a key selects one 32-byte block (one sector) with the high hash word and sets / tests one bit in each
+// of its eight 32-bit words (eight odd multipliers of the low hash word, the Parquet / Impala scheme).  ~8 bits per build key.
+__device__ __forceinline__ void bloom_masks(uint32_t h, uint32_t (&m)[8]) {
+    const uint32_t salt[8] = {0x47b6137bu, 0x44974d91u, 0x8824ad5bu, 0xa2b7289du, 0x705495c7u, 0x2df1424bu, 0x9efc4947u, 0x5c6bfb31u};
+#pragma unroll
+    for (int j = 0; j < 8; j++) m[j] = 1u << ((h * salt[j]) >> 27);
+}
+__global__ void join_bloom_add_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid_bytes, int64_t n, uint32_t* bloom, uint64_t n_blocks,
+                                      long long* minmax) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    long long mn = INT64_MAX, mx = INT64_MIN;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (key_valid_bytes && !key_valid_bytes[i]) continue;
+        const long long key = load_int_as_i64(key_data, key_ctype, i);
+        mn = key < mn ? key : mn; mx = key > mx ? key : mx;
+        const uint64_t h = xxh3_64_short((uint64_t)key, 8, SEED_HASH_JOIN);
+        uint32_t m[8];
+        bloom_masks((uint32_t)h, m);
+        uint32_t* blk = bloom + (size_t)(__umul64hi(h, n_blocks)) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) atomicOr(blk + j, m[j]);
+    }
+    for (int d = 16; d; d >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
+        mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0 && mn <= mx) { atomicMin(minmax, mn); atomicMax(minmax + 1, mx); }
+}
+// keep[i] = 1 iff row i can still find a partner: key not NA, inside [min, max] of the build keys, bloom hit
+__global__ void join_runtime_filter_kernel(const void* key_data, int key_ctype, const uint8_t* key_valid, int64_t n, const uint32_t* bloom, uint64_t n_blocks,
+                                           long long mn, long long mx, int use_minmax, int use_bloom, uint8_t* keep) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        bool k = bit_valid(key_valid, i);
+        if (k) {
+            const long long key = load_int_as_i64(key_data, key_ctype, i);
+            if (use_minmax && (key < mn || key > mx)) k = false;
+            if (k && use_bloom) {
+                const uint64_t h = xxh3_64_short((uint64_t)key, 8, SEED_HASH_JOIN);
+                uint32_t m[8];
+                bloom_masks((uint32_t)h, m);
+                const uint4* blk = reinterpret_cast<const uint4*>(bloom + (size_t)(__umul64hi(h, n_blocks)) * 8);
+                const uint4 lo = __ldg(blk), hi = __ldg(blk + 1);
+                k = (lo.x & m[0]) && (lo.y & m[1]) && (lo.z & m[2]) && (lo.w & m[3]) && (hi.x & m[4]) && (hi.y & m[5]) && (hi.z & m[6]) && (hi.w & m[7]);
+            }
+        }
+        keep[i] = k ? 1 : 0;
+    }
+}
+
 // ================================================================================================
 struct GrowCol {  // growable device column (geometric growth, copy on grow)
     DevBuf buf;
@@ -613,6 +670,15 @@ class JoinState {
     DevBuf d_slots32;                      // inline-payload table (all-8-byte bitmap-free build schema, <= 2 payload columns)
     bool fast_ready = false, inline_ready = false;
     int64_t inline_probes = 0, inline_builds = 0;
+    // join kind (set_kind, before the first build batch): mark join / probe-side anti join (reference: is_mark_join member,
+    // is_anti_join template argument of the probe)
+    bool mark = false, anti = false;
+    DevBuf d_mark, d_mark_valid;
+    // runtime join filter, built on demand from the build keys
+    DevBuf d_bloom, d_minmax;
+    uint64_t bloom_blocks = 0;
+    long long key_min = INT64_MAX, key_max = INT64_MIN;
+    int64_t filter_rows_in = 0, filter_rows_kept = 0;
     unsigned long long* h_cursor = nullptr;
     int64_t fast_probes = 0;
     Scanner scan;
@@ -653,6 +719,51 @@ class JoinState {
     ~JoinState() { cudaSetDevice(device); scratch_set_stream(stream); cudaStreamSynchronize(stream); pinned_release(h_cursor, 8); }
 
     int grid_for(int64_t n) const { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sms * 8)); }
+
+    void set_kind(bool is_mark, bool is_anti) {
+        B200_REQUIRE(n_build == 0 && !build_final, "b200 join: the join kind must be set before the first build batch");
+        B200_REQUIRE(!(is_mark && is_anti), "b200 join: a join is a mark join or an anti join, not both");
+        B200_REQUIRE(!(is_mark || is_anti) || !build_outer, "b200 join: mark / anti joins do not emit build rows (build_table_outer must be false)");
+        mark = is_mark; anti = is_anti;
+    }
+
+    // ---- runtime join filter ----
+    // n_blocks: 32-byte bloom blocks (0 = one per 32 build rows, ~8 bits per key); ranks that will OR their filters together
+    // pass the same value.  Also computes the min / max of the (non-NA) build keys.
+    void build_filter(uint64_t n_blocks) {
+        B200_REQUIRE(build_final, "b200 join: runtime filter before the build side was finished");
+        B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
+        bloom_blocks = n_blocks ? n_blocks : (uint64_t)n_build / 32 + 1;
+        d_bloom.alloc(bloom_blocks * 32);
+        B200_CUDA(cudaMemsetAsync(d_bloom.p, 0, bloom_blocks * 32, stream));
+        d_minmax.alloc(16);
+        const long long init[2] = {INT64_MAX, INT64_MIN};
+        B200_CUDA(cudaMemcpyAsync(d_minmax.p, init, 16, cudaMemcpyHostToDevice, stream));
+        if (n_build > 0) {
+            join_bloom_add_kernel<<<grid_for(n_build), 256, 0, stream>>>(bcol[0].buf.p, b_ct[0], b_has_valid[0] ? bvalid[0].buf.as<uint8_t>() : nullptr, n_build,
+                                                                        d_bloom.as<uint32_t>(), bloom_blocks, d_minmax.as<long long>());
+            launches++;
+            B200_CUDA(cudaGetLastError());
+        }
+        long long h[2];
+        B200_CUDA(cudaMemcpyAsync(h, d_minmax.p, 16, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA(cudaStreamSynchronize(stream));
+        key_min = h[0]; key_max = h[1];
+    }
+    void runtime_filter(const b200_table* t, int key_col, bool use_minmax, bool use_bloom, uint8_t* keep) {
+        B200_REQUIRE(t->device == device, "b200 join: runtime_filter takes a device-resident table on the state's device");
+        B200_REQUIRE(key_col >= 0 && key_col < t->n_cols, "b200 join: runtime_filter: bad key column");
+        B200_REQUIRE(ctype_size(t->cols[key_col].c_type) == ctype_size(b_ct[0]) && !ctype_is_float(t->cols[key_col].c_type), "b200 join: runtime_filter: key column type differs from the build key");
+        if (!d_bloom.p) build_filter(0);
+        B200_CUDA(cudaSetDevice(device));
+        const int64_t n = t->n_rows;
+        if (n == 0) return;
+        join_runtime_filter_kernel<<<grid_for(n), 256, 0, stream>>>(t->cols[key_col].data, t->cols[key_col].c_type, t->cols[key_col].validity, n, d_bloom.as<uint32_t>(),
+                                                                   bloom_blocks, key_min, key_max, use_minmax ? 1 : 0, use_bloom ? 1 : 0, keep);
+        launches++;
+        B200_CUDA(cudaGetLastError());
+        filter_rows_in += n;
+    }
 
     // device pointers for a batch (host batches are staged to the device first)
     void stage_batch(const b200_table* t, int ncols, const std::vector<int8_t>& cts, std::vector<const void*>& data,
@@ -753,7 +864,7 @@ class JoinState {
         cap = 1024;
         while (cap < 2ull * (uint64_t)n_build) cap <<= 1;
         uint64_t n_slots = cap + 2;
-        if (try_inline_build(n_slots)) {
+        if (!mark && !anti && try_inline_build(n_slots)) {
             d_goffs.alloc(8); d_groups.alloc(8);
             fast_ready = true; inline_ready = true; inline_builds++;
             build_final = true;
@@ -782,7 +893,7 @@ class JoinState {
                 launches++;
             }
             d_cnt_multi.release(); d_fill.release(); d_row_slot.release();
-            if (n_multi == 0 && !build_outer && !probe_outer && n_b >= 1) {
+            if (n_multi == 0 && !build_outer && !probe_outer && !mark && !anti && n_b >= 1) {
                 // every key (incl. the NA / marker groups) has exactly one build row: set up the fused probe path
                 d_slots16.alloc(n_slots * sizeof(Slot16));
                 join_make_slots16_kernel<<<grid_for((int64_t)n_slots), 256, 0, stream>>>(d_tkeys.as<long long>(), d_info.as<SlotInfo>(), n_slots, d_slots16.as<Slot16>());
@@ -912,7 +1023,8 @@ class JoinState {
         for (int64_t k = 0; k < n_kb; k++) { B200_REQUIRE((int)kept_b[k] < n_b, "b200 join: bad kept build column"); kb.push_back((int)kept_b[k]); }
         for (int64_t k = 0; k < n_kp; k++) { B200_REQUIRE((int)kept_p[k] < n_p, "b200 join: bad kept probe column"); kp.push_back((int)kept_p[k]); }
         int n_out_cols = (int)(kb.size() + kp.size());
-        B200_REQUIRE(n_out_cols <= J_MAX_COLS, "b200 join: too many output columns");
+        B200_REQUIRE(n_out_cols + (mark ? 1 : 0) <= J_MAX_COLS, "b200 join: too many output columns");
+        B200_REQUIRE(!mark || kb.empty(), "b200 join: a mark join does not output build table columns (bodo/pandas/physical/join.h:309-316)");
         int64_t n = t->n_rows;
         std::vector<const void*> data; std::vector<const uint8_t*> valid;
         stage_batch(t, n_p, p_ct, data, valid);
@@ -921,8 +1033,10 @@ class JoinState {
         unsigned long long n_match = 0;
         d_pslot.ensure((size_t)(n + 1) * 4); d_pcnt.ensure((size_t)(n + 1) * 4); d_poff.ensure((size_t)(n + 2) * 8);
         if (n > 0) {
+            if (mark) { d_mark.ensure((size_t)n + 32); d_mark_valid.ensure((size_t)(n + 7) / 8 + 32); B200_CUDA(cudaMemsetAsync(d_mark_valid.p, 0xff, (size_t)(n + 7) / 8 + 8, stream)); }
             join_probe_count_kernel<<<grid_for(n), 256, 0, stream>>>(data[0], p_ct[0], valid[0], n, d_tkeys.as<long long>(), cap, d_info.as<SlotInfo>(),
-                                                                     probe_outer ? 1 : 0, d_pslot.as<uint32_t>(), d_pcnt.as<uint32_t>(), na_equal ? 1 : 0);
+                                                                     probe_outer ? 1 : 0, d_pslot.as<uint32_t>(), d_pcnt.as<uint32_t>(), na_equal ? 1 : 0,
+                                                                     anti ? 1 : (mark ? 2 : 0), mark ? d_mark.as<uint8_t>() : nullptr);
             launches++;
             B200_CUDA(cudaMemsetAsync(d_pcnt.as<uint32_t>() + n, 0, 4, stream));
             n_match = scan.run(d_pcnt.as<uint32_t>(), n + 1, d_poff.as<unsigned long long>(), stream, &launches);
@@ -938,7 +1052,7 @@ class JoinState {
         for (int k = 0; k < n_out_cols; k++) {
             bool is_b = k < (int)kb.size();
             int src = is_b ? kb[k] : kp[k - kb.size()];
-            out_has_valid[k] = is_b ? (b_has_valid[src] || b_at[src] == ARR_NULLABLE || probe_outer)
+            out_has_valid[k] = is_b ? (b_has_valid[src] || b_at[src] == ARR_NULLABLE || probe_outer || anti)
                                     : (valid[src] != nullptr || p_at[src] == ARR_NULLABLE || build_outer);
         }
         auto ensure_out = [&](int64_t rows) {
@@ -1027,6 +1141,11 @@ class JoinState {
         B200_CUDA(cudaGetLastError());
         B200_CUDA(cudaStreamSynchronize(stream));
         describe_out(out, kb, kp, rows);
+        if (mark) {  // the mark column: BOOL, nullable array type, every row valid; output row i is probe row i
+            b200_column& c = out->cols[n_out_cols];
+            c.data = d_mark.p; c.validity = d_mark_valid.as<uint8_t>(); c.length = rows; c.c_type = CT_BOOL; c.arr_type = ARR_NULLABLE;
+            out->n_cols = n_out_cols + 1;
+        }
         probe_rows += n; out_rows_total += rows;
         return rows;
     }
@@ -1074,6 +1193,42 @@ int b200_join_probe_consume_batch(void* state, const b200_table* in_table, const
 }
 
 void b200_delete_join_state(void* state) { delete (JoinState*)state; }
+
+int b200_join_set_kind(void* state, int32_t is_mark_join, int32_t is_anti_join) {
+    try {
+        B200_REQUIRE(state, "b200 join: null state");
+        ((JoinState*)state)->set_kind(is_mark_join != 0, is_anti_join != 0);
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+int b200_join_build_filter(void* state, int64_t n_bloom_blocks, void** bloom_words_dev, int64_t* n_blocks_out, int64_t* key_min_max) {
+    try {
+        B200_REQUIRE(state && n_bloom_blocks >= 0, "b200 join: bad arguments");
+        auto* s = (JoinState*)state;
+        s->build_filter((uint64_t)n_bloom_blocks);
+        if (bloom_words_dev) *bloom_words_dev = s->d_bloom.p;
+        if (n_blocks_out) *n_blocks_out = (int64_t)s->bloom_blocks;
+        if (key_min_max) { key_min_max[0] = s->key_min; key_min_max[1] = s->key_max; }
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+int b200_join_set_key_bounds(void* state, int64_t key_min, int64_t key_max) {
+    try {
+        B200_REQUIRE(state, "b200 join: null state");
+        ((JoinState*)state)->key_min = key_min; ((JoinState*)state)->key_max = key_max;
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
+
+int b200_join_runtime_filter(void* state, const b200_table* in_table, int32_t key_col, int32_t use_min_max, int32_t use_bloom, uint8_t* keep_out) {
+    try {
+        B200_REQUIRE(state && in_table && keep_out, "b200 join: null argument");
+        ((JoinState*)state)->runtime_filter(in_table, key_col, use_min_max != 0, use_bloom != 0, keep_out);
+        return 0;
+    } catch (const std::exception& e) { b200::set_last_error(e.what()); return -1; }
+}
 
 int64_t b200_join_get_metric(void* state, int32_t which) {
     auto* s = (JoinState*)state;

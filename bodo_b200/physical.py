@@ -171,6 +171,18 @@ class PhysicalFilterProject:
         return res, (OperatorResult.FINISHED if prev == OperatorResult.FINISHED else OperatorResult.NEED_MORE_INPUT)
 
 
+def filter_project_table(table: Table, keep) -> Table:
+    """Rows of a device-resident `table` whose entry in `keep` (uint8 device tensor, one byte per row) is non-zero, through the
+    fused filter kernel (used by streaming.join.runtime_join_filter)."""
+    from .expr import col
+    from .table import ArrTypes, Column, CTypes
+
+    ext = Table(list(table.columns) + [Column(keep, None, CTypes.BOOL, ArrTypes.NUMPY, table.n_rows)], list(table.names) + ["__keep"])
+    op = PhysicalFilterProject(col("__keep"), [(n, col(n)) for n in table.names], device=table.device)
+    out, _ = op.ProcessBatch(ext, OperatorResult.NEED_MORE_INPUT)
+    return out
+
+
 class PhysicalReadArrowDevice:
     """Source over an in-memory pyarrow Table that hands out DEVICE batches; string columns named in `dict_builders`
     ({column: DictionaryBuilder}) travel as dictionary ids unified against the builder (bodo_b200.dictionary), everything else
@@ -235,6 +247,10 @@ class PhysicalJoin:
     def __init__(self, build_key: int, probe_key: int, build_names, probe_names, how: str = "inner", **kw):
         build_outer = how in ("right", "outer")   # the build side is the RIGHT table (reference convention)
         probe_outer = how in ("left", "outer")
+        if how == "anti":   # LEFT ANTI: probe rows without a partner (physical/join.h:151: no build columns in the output)
+            kw["is_anti_join"] = True
+        elif how == "mark":
+            kw["is_mark_join"] = True
         kw.setdefault("is_na_equal", True)  # pandas merge semantics: NA joins NA (bodo/pandas/physical/join.h:267)
         self.state = J.init_join_state(-1, (build_key,), (probe_key,), tuple(build_names), tuple(probe_names), build_outer, probe_outer, **kw)
 

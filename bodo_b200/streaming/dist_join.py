@@ -145,7 +145,7 @@ class DistJoinState:
 
     def __init__(self, operator_id, build_key_inds, probe_key_inds, build_colnames, probe_colnames, build_outer, probe_outer,
                  output_batch_size, expected_build_rows, device, stream, is_na_equal=False, build_parallel=False, probe_parallel=False,
-                 force_broadcast=False, process_group=None):
+                 force_broadcast=False, process_group=None, is_mark_join=False, is_anti_join=False):
         import torch
         import torch.distributed as dist
 
@@ -160,7 +160,13 @@ class DistJoinState:
         self.build_outer = bool(build_outer)
         self.device = device if device is not None else torch.cuda.current_device()
         self.local = J.JoinState(operator_id, build_key_inds, probe_key_inds, build_colnames, probe_colnames, build_outer, probe_outer,
-                                 output_batch_size, expected_build_rows, self.device, stream, is_na_equal=is_na_equal)
+                                 output_batch_size, expected_build_rows, self.device, stream, is_na_equal=is_na_equal,
+                                 is_mark_join=is_mark_join, is_anti_join=is_anti_join)
+        self.probe_outer = bool(probe_outer)
+        # bloom filter + key bounds over the build keys of ALL ranks, applied to probe rows before they are shuffled (the
+        # reference's use_bloom_filter probe path, _join.cpp:3460-3600); B200_JOIN_BLOOM=0 disables it
+        self.use_filter = os.environ.get("B200_JOIN_BLOOM", "1") != "0" and not probe_outer and not is_mark_join and not is_anti_join
+        self.filter_ready = False
         self._build_batches = []
         self.is_broadcast = False
         self.build_key = self.local.build_key_inds[0]
@@ -231,12 +237,42 @@ class DistJoinState:
         else:
             mine = self._shuffle(whole, self.build_key)
         self.metrics["build_rows_local"] = mine.n_rows
-        return J.join_build_consume_batch(self.local, mine, True)
+        res = J.join_build_consume_batch(self.local, mine, True)
+        if self.use_filter and self.probe_parallel and not self.is_broadcast:
+            self._build_global_filter()
+        return res
+
+    def _build_global_filter(self):
+        """Union of the ranks' bloom filters (same block count everywhere) and the global key bounds."""
+        import torch
+        import torch.distributed as dist
+
+        dev = torch.device("cuda", self.device)
+        tot = torch.tensor([self.metrics["build_rows_local"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, group=self.group)
+        n_blocks = int(tot.item()) // 32 + 1
+        words, (mn, mx) = J.build_runtime_filter(self.local, n_blocks)
+        gathered = torch.empty(self.n_pes * words.numel(), dtype=words.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, words, group=self.group)  # NCCL has no bitwise-or reduction
+        acc = gathered.view(self.n_pes, -1)[0].clone()
+        for r in range(1, self.n_pes):
+            acc |= gathered.view(self.n_pes, -1)[r]
+        words.copy_(acc)
+        lo = torch.tensor([mn], dtype=torch.int64, device=dev)
+        hi = torch.tensor([mx], dtype=torch.int64, device=dev)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        _lib.check(_lib.lib().b200_join_set_key_bounds(self.local.handle, int(lo.item()), int(hi.item())), "runtime_join_filter")
+        self.filter_ready = True
+        self.metrics["filter"] = 1
 
     def probe_consume(self, table: Table, is_last: bool, produce_output: bool = True, used_cols=None):
         self.metrics["probe_rows_in"] += table.n_rows
         partitioned_build = self.build_parallel and not self.is_broadcast
         if partitioned_build and self.probe_parallel:
+            if self.filter_ready and table.n_rows:
+                table = J.runtime_join_filter((self,), to_device(table, self.device), ((self.probe_key,),))
+                self.metrics["probe_rows_after_filter"] = self.metrics.get("probe_rows_after_filter", 0) + table.n_rows
             table = self._shuffle(table, self.probe_key)
         elif partitioned_build:
             table = self._owned_only(table, self.probe_key)

@@ -162,6 +162,25 @@ int b200_join_probe_consume_batch(void* state, const b200_table* in_table,
 
 /* delete_join_state (_join.cpp:4429). */
 void b200_delete_join_state(void* state);
+/* Join kind, to be called between init and the first build batch: mark join (HashJoinState::is_mark_join, _join.h:402 — every
+ * probe row goes out once, no build columns, plus one trailing BOOL column "has a match": `out->cols` needs n_kept_probe + 1
+ * descriptors) or probe-side anti join (the is_anti_join template argument of the reference's probe, _join.cpp:763-767 — a probe
+ * row goes out, with NULL build columns, iff no build row matches).  build_table_outer must be false for both. */
+int b200_join_set_kind(void* state, int32_t is_mark_join, int32_t is_anti_join);
+
+/* Runtime join filter (HashJoinState::RuntimeFilter, _join.h:1060-1095; bloom filter bodo/libs/gpu_bloom_filter.cu:60-201; key
+ * min / max _join.cpp:3199-3238), available once the build side is complete.
+ * b200_join_build_filter builds a split-block bloom filter over the build keys (n_bloom_blocks 32-byte blocks, 0 = one per 32 build
+ * rows) and their min / max; it returns the device address of the filter words (n_blocks * 8 uint32) so that the ranks of a sharded
+ * join can OR their filters together in place (all ranks pass the same n_bloom_blocks; b200_join_set_key_bounds installs the
+ * reduced bounds).  b200_join_runtime_filter writes keep_out[i] = 1 for the rows of a DEVICE-resident table that can still find a
+ * partner (key not NA, inside the bounds, bloom hit): the rows a probe-side scan may drop before they are shuffled or probed
+ * (inner and build-outer joins only — an outer probe side must keep its rows). */
+int b200_join_build_filter(void* state, int64_t n_bloom_blocks, void** bloom_words_dev, int64_t* n_blocks_out, int64_t* key_min_max);
+int b200_join_set_key_bounds(void* state, int64_t key_min, int64_t key_max);
+int b200_join_runtime_filter(void* state, const b200_table* in_table, int32_t key_col, int32_t use_min_max, int32_t use_bloom,
+                             uint8_t* keep_out);
+
 /* Operator metrics (the reference's JoinMetrics, bodo/libs/streaming/_join.h): 0 build rows, 1 hash-table slots, 2 probe rows,
  * 3 output rows, 4 kernel launches, 5 probe batches through a fused (unique-build-key) probe kernel, 6 of those through the
  * inline-payload kernel (key + payload in one 32-byte slot), 7 inline-payload table builds. */

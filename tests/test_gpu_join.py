@@ -185,3 +185,70 @@ def test_inline_payload_probe_matches_oracle(gpu_lib, oracle, n_payload, monkeyp
     got3, used3 = run()
     assert used3 == 0
     assert_rowset_equal(got3, exp)
+
+
+@pytest.mark.parametrize("is_na_equal", [False, True])
+@pytest.mark.parametrize("to_device", [False, True])
+def test_anti_and_mark_joins_vs_pandas(gpu_lib, is_na_equal, to_device):
+    """LEFT ANTI (probe rows without a partner, NULL build columns dropped by the caller) and MARK joins (every probe row + a
+    boolean "has a partner" column), reference: is_anti_join / is_mark_join of HashJoinState (_join.cpp:763-767, 3668-3693).
+    Duplicated build keys must not duplicate output rows; NA probe keys match NA build keys only under is_na_equal."""
+    rng = np.random.default_rng(21)
+    nb, npr = 5_000, 40_000
+    build = pd.DataFrame({"k": pd.array(rng.integers(0, 3_000, nb), dtype="Int64"), "b1": rng.integers(0, 100, nb)})
+    build.loc[::500, "k"] = pd.NA
+    probe = pd.DataFrame({"k": pd.array(rng.integers(0, 6_000, npr), dtype="Int64"), "p1": rng.random(npr), "p2": rng.integers(0, 1 << 40, npr)})
+    probe.loc[::777, "k"] = pd.NA
+    pna = probe.k.isna().to_numpy()
+    has = np.where(pna, is_na_equal, probe.k.fillna(-1).isin(build.k.dropna()).to_numpy())
+
+    def run(**kind):
+        bt, pt = Table.from_pandas(build), Table.from_pandas(probe)
+        st = init_join_state(-1, (0,), (0,), tuple(build.columns), tuple(probe.columns), False, False, is_na_equal=is_na_equal, **kind)
+        join_build_consume_batch(st, table_to_device(bt) if to_device else bt, True)
+        outs = []
+        for i0 in range(0, npr, 15_000):
+            p = pt.slice(i0, i0 + 15_000)
+            out, _, _ = join_probe_consume_batch(st, table_to_device(p) if to_device else p, i0 + 15_000 >= npr, True, ([], [0, 1, 2]))
+            outs.append(out.to_pandas())
+        delete_join_state(st)
+        return pd.concat(outs, ignore_index=True)
+
+    anti = run(is_anti_join=True)
+    exp_anti = probe[~has].reset_index(drop=True)
+    assert_rowset_equal(anti, exp_anti)
+    markdf = run(is_mark_join=True)
+    assert markdf.shape == (npr, 4)
+    # a mark join keeps the probe rows in order: row i of the output is probe row i
+    np.testing.assert_array_equal(markdf.iloc[:, 3].to_numpy(dtype=bool), has)
+    np.testing.assert_array_equal(markdf.iloc[:, 2].to_numpy(dtype=np.int64), probe.p2.to_numpy())
+
+
+def test_runtime_join_filter_has_no_false_negatives(gpu_lib):
+    """runtime_join_filter (bodo/libs/streaming/join.py:1392-1415): rows outside the build keys' [min, max] and bloom misses are
+    dropped before the probe; no row with a partner may be lost, and the false-positive rate of the ~8 bits / key split-block
+    bloom filter stays small."""
+    from bodo_b200.streaming.join import build_runtime_filter, runtime_join_filter
+    rng = np.random.default_rng(4)
+    nb, npr = 200_000, 1_000_000
+    bk = rng.choice(np.arange(1_000_000, 3_000_000), nb, replace=False).astype(np.int64)
+    build = pd.DataFrame({"k": bk, "b1": rng.integers(0, 100, nb)})
+    pk = rng.integers(0, 4_000_000, npr).astype(np.int64)
+    probe = pd.DataFrame({"p0": rng.random(npr), "k": pd.array(pk, dtype="Int64")})
+    probe.loc[::1000, "k"] = pd.NA
+    st = init_join_state(-1, (0,), (1,), tuple(build.columns), tuple(probe.columns), False, False)
+    join_build_consume_batch(st, table_to_device(Table.from_pandas(build)), True)
+    words, (mn, mx) = build_runtime_filter(st)
+    assert (mn, mx) == (int(bk.min()), int(bk.max())) and words.numel() == (nb // 32 + 1) * 8
+    kept = runtime_join_filter((st,), table_to_device(Table.from_pandas(probe)), ((1,),)).to_pandas()
+    partner = probe.k.isin(bk).fillna(False).to_numpy()
+    kept_keys = kept.iloc[:, 1].to_numpy(dtype="float64", na_value=np.nan)
+    assert np.isin(pk[partner], kept_keys[~np.isnan(kept_keys)].astype(np.int64)).all()
+    assert len(kept) >= partner.sum() and not np.isnan(kept_keys).any()
+    in_range = (pk >= mn) & (pk <= mx) & ~probe.k.isna().to_numpy()
+    false_pos = len(kept) - partner.sum()
+    assert false_pos <= 0.08 * (in_range.sum() - partner.sum()), (false_pos, in_range.sum(), partner.sum())
+    # the join over the filtered rows equals the join over all rows
+    out_f, _, _ = join_probe_consume_batch(st, kept_table := runtime_join_filter((st,), table_to_device(Table.from_pandas(probe)), ((1,),)), True, True)
+    delete_join_state(st)
+    assert out_f.n_rows == partner.sum()

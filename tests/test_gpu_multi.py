@@ -208,6 +208,8 @@ def _join_worker(rank, world, port, q):
                 bcast = [m["broadcast"] for m in allm]
                 moved = sum(m["build_rows_local"] for m in allm)
                 results[name] = (ok, bcast, moved)
+                results[name + "/filter"] = ([m.get("filter", 0) for m in allm], sum(m.get("probe_rows_after_filter", 0) for m in allm),
+                                             int((pi >= 0).sum() if False else np.isin(probe.k.to_numpy(), build.k.to_numpy()).sum()))
         q.put((rank, results))
     except Exception:
         import traceback
@@ -238,6 +240,11 @@ def test_sharded_join_shuffle_and_broadcast_nccl(gpu_lib):
         assert isinstance(r[1], dict), r
     ok, bcast, moved = r0[1]["shuffle"]
     assert ok and bcast == [0] * world and moved == 40_000, r0  # partitioned: every build row lives on exactly one rank
+    # inner sharded join: the ranks' bloom filters were OR-ed and applied before the probe shuffle (keys >= 30 000 are outside the
+    # build keys' bounds): fewer rows travel, none that has a partner is lost (the join result above is complete)
+    flags, after, with_partner = r0[1]["shuffle/filter"]
+    assert flags == [1] * world and with_partner <= after < 150_000 * 0.8, r0[1]["shuffle/filter"]
+    assert r0[1]["shuffle-outer/filter"][0] == [0] * world  # an outer probe side keeps its rows
     ok, bcast, moved = r0[1]["shuffle-outer"]
     assert ok and bcast == [0] * world, r0
     ok, bcast, moved = r0[1]["broadcast"]
