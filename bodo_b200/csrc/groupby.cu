@@ -29,6 +29,9 @@ constexpr int64_t CHUNK_ROWS = 1ll << 27;  // rows per kernel launch (bounds the
 
 enum OpKind : int { K_SUM_I64 = 0, K_SUM_F64, K_COUNT, K_SIZE, K_MEAN, K_MIN_I64, K_MAX_I64, K_MIN_F64, K_MAX_F64,
                     K_SUMSQ_F64, K_SUMCUBE_F64,  // hidden accumulators: sum of squares / cubes (as double) of the non-NA values
+                    // first / last non-NA value in row order (aggfunc<first / last>, _groupby_agg_funcs.h:594-611): a0 = value
+                    // bits, a1 = sequence number of the row that supplied it (see groupby_firstlast_fix_kernel)
+                    K_FIRST, K_LAST,
                     // evaluation-only kinds of composite functions (accumulators: a K_MEAN pair + K_SUMSQ (+ K_SUMCUBE))
                     E_VAR, E_STD, E_VAR_POP, E_STD_POP, E_SKEW };
 
@@ -53,6 +56,7 @@ struct ConsumeArgs {
     long long* counters;  // [0] groups in table, [1] failed rows, [2] cursor, [3] NA present, [4] EMPTY_KEY present
     long long group_limit;
     uint32_t* fail_list;
+    unsigned long long seq_base;  // first / last: sequence number of row 0 of this launch, minus 1 (rank << 44 | rows consumed so far)
     int n_ops;
     OpDesc ops[MAX_OPS];
 };
@@ -86,6 +90,29 @@ __device__ __forceinline__ uint64_t find_or_insert(long long* __restrict__ tkeys
         s = (s + 1) & mask;
     }
     return ~0ull;
+}
+
+// lookup only; UINT64_MAX when the key is not in the table
+__device__ __forceinline__ uint64_t find_only(const long long* __restrict__ tkeys, uint64_t cap, long long key) {
+    uint64_t mask = cap - 1;
+    uint64_t s = (key_hash(key) >> 32) & mask;
+    for (uint64_t probes = 0; probes <= mask; probes++) {
+        long long k = __ldcg(tkeys + s);
+        if (k == key) return s;
+        if (k == EMPTY_KEY) return ~0ull;
+        s = (s + 1) & mask;
+    }
+    return ~0ull;
+}
+// value of a first / last input as the 8 bytes kept in the accumulator (integers sign / zero extended, floats as double)
+__device__ __forceinline__ bool firstlast_value(const OpDesc& op, int64_t row, unsigned long long& bits) {
+    if (op.in_ctype == CT_FLOAT64 || op.in_ctype == CT_FLOAT32) {
+        const double v = load_as_f64(op.in_data, op.in_ctype, row);
+        bits = (unsigned long long)__double_as_longlong(v);
+        return !isnan(v);
+    }
+    bits = (unsigned long long)load_int_as_i64(op.in_data, op.in_ctype, row);
+    return true;
 }
 
 template <typename A>
@@ -124,6 +151,15 @@ __device__ __forceinline__ void apply_ops(const A& a, uint64_t slot, int64_t row
             case K_SUMSQ_F64: case K_SUMCUBE_F64: {  // skew_agg's m2 / m3 (:723-745); var / std use m2 with the K_MEAN pair
                 double v = load_as_f64(op.in_data, op.in_ctype, row);
                 if (!isnan(v)) atomicAdd((double*)op.a0 + slot, op.kind == K_SUMSQ_F64 ? v * v : v * v * v);
+                break;
+            }
+            case K_FIRST: case K_LAST: {  // phase 1: which row supplies the value (phase 2 writes it, groupby_firstlast_fix_kernel)
+                unsigned long long bits;
+                if (firstlast_value(op, row, bits)) {
+                    const unsigned long long seq = a.seq_base + (unsigned long long)row + 1ull;
+                    if (op.kind == K_FIRST) atomicMin((unsigned long long*)op.a1 + slot, seq);
+                    else atomicMax((unsigned long long*)op.a1 + slot, seq);
+                }
                 break;
             }
             case K_MIN_I64:
@@ -180,6 +216,30 @@ __global__ void __launch_bounds__(256) groupby_consume_kernel(const __grid_const
             }
         }
         apply_ops(a, slot, row);
+    }
+}
+
+// first / last, phase 2 (after every row of the launch — replays included — has been applied): the row whose sequence number
+// won the atomicMin / atomicMax writes its value.  Two passes because (value, sequence) cannot be updated by one atomic.
+__global__ void __launch_bounds__(256) groupby_firstlast_fix_kernel(const __grid_constant__ ConsumeArgs a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < a.n_rows; row += stride) {
+        uint64_t slot;
+        if (!bit_valid(a.key_valid, row)) { if (a.dropna) continue; slot = a.cap; }
+        else {
+            const long long key = load_int_as_i64(a.key_data, a.key_ctype, row);
+            slot = key == EMPTY_KEY ? a.cap + 1 : find_only(a.tkeys, a.cap, key);
+            if (slot == ~0ull) continue;
+        }
+        const unsigned long long seq = a.seq_base + (unsigned long long)row + 1ull;
+#pragma unroll 1
+        for (int j = 0; j < a.n_ops; j++) {
+            const OpDesc& op = a.ops[j];
+            if (op.kind != K_FIRST && op.kind != K_LAST) continue;
+            if (!bit_valid(op.in_valid, row)) continue;
+            unsigned long long bits;
+            if (firstlast_value(op, row, bits) && ((const unsigned long long*)op.a1)[slot] == seq) ((unsigned long long*)op.a0)[slot] = bits;
+        }
     }
 }
 
@@ -383,6 +443,16 @@ __global__ void eval_output_kernel(const __grid_constant__ EvalArgs a) {
                         store_f_typed(op.out_data, op.out_ctype, p, r);
                         break;
                     }
+                    case K_FIRST: case K_LAST: {  // NA when the group never saw a non-NA value (nullable / float outputs)
+                        const unsigned long long q = ((const unsigned long long*)op.a1)[s];
+                        const bool seen = op.kind == K_FIRST ? q != ~0ull : q != 0ull;
+                        const unsigned long long bits = ((const unsigned long long*)op.a0)[s];
+                        valid = seen;
+                        if (op.out_ctype == CT_FLOAT32 || op.out_ctype == CT_FLOAT64)
+                            store_f_typed(op.out_data, op.out_ctype, p, seen ? __longlong_as_double((long long)bits) : __longlong_as_double(0x7ff8000000000000ll));
+                        else store_int_typed(op.out_data, op.out_ctype, p, seen ? (long long)bits : 0);
+                        break;
+                    }
                     case K_MIN_I64: case K_MAX_I64: {
                         if (op.a1) valid = ((const unsigned long long*)op.a1)[s] > 0;
                         store_int_typed(op.out_data, op.out_ctype, p, valid ? ((const long long*)op.a0)[s] : 0);
@@ -483,8 +553,13 @@ __device__ __forceinline__ void combine_apply(const CombineArgs& a, uint64_t slo
                 case K_MAX_I64: atomicMax((long long*)a.a0[j] + slot, (long long)v0); break;
                 case K_MIN_F64: atomicMin((unsigned long long*)a.a0[j] + slot, v0); break;
                 case K_MAX_F64: atomicMax((unsigned long long*)a.a0[j] + slot, v0); break;
+                // first / last: the partial with the smallest / largest sequence number wins (sequence numbers carry the rank in
+                // their high bits: rank order, then row order, as the reference's rank-ordered combine); its value is written by
+                // combine_firstlast_fix_kernel once every partial of the batch has been applied
+                case K_FIRST: if (v1 != ~0ull) atomicMin((unsigned long long*)a.a1[j] + slot, v1); break;
+                case K_LAST: if (v1 != 0ull) atomicMax((unsigned long long*)a.a1[j] + slot, v1); break;
             }
-            if (a.a1[j] && a.kinds[j] != K_MEAN) atomicAdd((unsigned long long*)a.a1[j] + slot, v1);
+            if (a.a1[j] && a.kinds[j] != K_MEAN && a.kinds[j] != K_FIRST && a.kinds[j] != K_LAST) atomicAdd((unsigned long long*)a.a1[j] + slot, v1);
         }
     }
 }
@@ -509,6 +584,34 @@ __global__ void combine_partials_kernel(const __grid_constant__ CombineArgs a) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_rows; i += stride)
         combine_one_row(a, a.index_list ? (int64_t)a.index_list[i] : i);
+}
+// first / last, phase 2 of the combine step: the partial whose sequence number won writes its value
+__device__ __forceinline__ void combine_firstlast_fix_row(const CombineArgs& a, int64_t row) {
+    const unsigned long long* r = a.in + row * a.row_words;
+    const long long key = (long long)r[0];
+    uint64_t slot;
+    if (!(r[1] & 1)) slot = a.cap;
+    else if (key == EMPTY_KEY) slot = a.cap + 1;
+    else { slot = find_only(a.tkeys, a.cap, key); if (slot == ~0ull) return; }
+    int w = 2;
+    for (int j = 0; j < a.n_ops; j++) {
+        const unsigned long long v0 = r[w++];
+        const unsigned long long v1 = a.a1[j] ? r[w++] : 0;
+        if ((a.kinds[j] == K_FIRST && v1 != ~0ull) || (a.kinds[j] == K_LAST && v1 != 0ull))
+            if (((const unsigned long long*)a.a1[j])[slot] == v1) ((unsigned long long*)a.a0[j])[slot] = v0;
+    }
+}
+__global__ void combine_firstlast_fix_kernel(const __grid_constant__ CombineArgs a, const unsigned long long* hdr, int n_pes, long long cap_rows) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (hdr == nullptr) {  // one contiguous run of partial rows
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_rows; i += stride) combine_firstlast_fix_row(a, i);
+        return;
+    }
+    for (int s = 0; s < n_pes; s++) {  // the segments of a receive slab (see xchg_combine_slab_kernel)
+        if (hdr[s] >> 63) return;  // overflow flag: nobody combined
+        const int64_t n = (int64_t)(hdr[s] & ~(1ull << 63));
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) combine_firstlast_fix_row(a, (int64_t)s * cap_rows + i);
+    }
 }
 
 // ---- fused exchange: pack + all-to-all in ONE kernel over peer memory (NVLink stores), combine straight out of the slab ----
@@ -610,6 +713,7 @@ struct MkArgs {
     uint32_t* fail_list;
     int n_ops;
     OpDesc ops[MAX_OPS];
+    unsigned long long seq_base;  // unused (first / last are single-key only); apply_ops reads it
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -1631,6 +1735,7 @@ struct FuncSpec {
     int out_arrtype;
     bool has_a1;
     unsigned long long init0;
+    unsigned long long init1 = 0;  // initial value of the second accumulator
 };
 
 class GroupbyState {
@@ -1645,6 +1750,7 @@ class GroupbyState {
     int n_outs = 0;               // aggregates the caller asked for (output columns)
     std::vector<OutSpec> outs;
     bool dropna, parallel;
+    bool has_firstlast = false;
     int n_pes, rank;
     int64_t output_batch_size;
     int sms;
@@ -1747,6 +1853,13 @@ class GroupbyState {
                     else f.init0 = mn ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
                     break;
                 }
+                case FT_FIRST: case FT_LAST:
+                    B200_REQUIRE(nk == 1, "b200 groupby: first / last are supported for single-column keys");
+                    f.kind = f.ftype == FT_FIRST ? K_FIRST : K_LAST;
+                    f.out_ctype = f.in_ctype; f.out_arrtype = f.in_arrtype;
+                    f.has_a1 = true; f.init1 = f.ftype == FT_FIRST ? ~0ull : 0ull;
+                    has_firstlast = true;
+                    break;
                 case FT_VAR: case FT_STD: case FT_VAR_POP: case FT_STD_POP: case FT_SKEW: {
                     // composite: a K_MEAN pair (sum, count) + sum of squares (+ sum of cubes), all over the same input column
                     OutSpec o{};
@@ -1770,7 +1883,7 @@ class GroupbyState {
                 }
                 default:
                     throw Error("b200 groupby: unsupported aggregate function ftype=" + std::to_string(f.ftype) +
-                                " (supported: size, sum, count, mean, min, max, var, std, var_pop, std_pop, skew)");
+                                " (supported: size, sum, count, mean, min, max, first, last, var, std, var_pop, std_pop, skew)");
             }
             OutSpec o{};
             o.ftype = f.ftype; o.kind = f.kind; o.prim[0] = (int)funcs.size(); o.n_prim = 1; o.out_ctype = f.out_ctype; o.out_arrtype = f.out_arrtype;
@@ -1831,7 +1944,7 @@ class GroupbyState {
         for (int j = 0; j < n_funcs; j++) {
             a0[j].alloc((c + 2) * 8);
             fill(a0[j].p, c + 2, funcs[j].init0);
-            if (funcs[j].has_a1) { a1[j].alloc((c + 2) * 8); fill(a1[j].p, c + 2, 0); }
+            if (funcs[j].has_a1) { a1[j].alloc((c + 2) * 8); fill(a1[j].p, c + 2, funcs[j].init1); }
         }
     }
 
@@ -2460,17 +2573,7 @@ class GroupbyState {
                 else
                     groupby_consume_i64_sumcount_kernel<false, true><<<g, 256, 0, stream>>>(k, v, rows, d_keys.as<long long>(), cap, as, ac, ctr, limit, d_fail.as<uint32_t>());
             } else {
-                ConsumeArgs a{};
-                a.key_data = data[0]; a.key_valid = valid[0]; a.key_ctype = c_types[0]; a.dropna = dropna ? 1 : 0;
-                a.n_rows = rows; a.index_list = index_list; a.tkeys = d_keys.as<long long>(); a.cap = cap;
-                a.counters = ctr; a.group_limit = limit; a.fail_list = d_fail.as<uint32_t>(); a.n_ops = n_funcs;
-                for (int j = 0; j < n_funcs; j++) {
-                    const FuncSpec& f = funcs[j];
-                    a.ops[j].kind = f.kind; a.ops[j].in_ctype = f.in_ctype;
-                    a.ops[j].in_data = f.in_col >= 0 ? data[f.in_col] : nullptr;
-                    a.ops[j].in_valid = f.in_col >= 0 ? valid[f.in_col] : nullptr;
-                    a.ops[j].a0 = d_a0[j].p; a.ops[j].a1 = f.has_a1 ? d_a1[j].p : nullptr;
-                }
+                ConsumeArgs a = generic_args(data, valid, index_list, rows);
                 groupby_consume_kernel<<<grid_for(rows), 256, 0, stream>>>(a);
             }
             launches++;
@@ -2480,9 +2583,30 @@ class GroupbyState {
         };
         launch(nullptr, n);
         settle(n, could_fail, launch);
+        if (has_firstlast) {  // every row is in (replays included): the rows that won first / last write their values
+            groupby_firstlast_fix_kernel<<<grid_for(n), 256, 0, stream>>>(generic_args(data, valid, nullptr, n));
+            launches++;
+            B200_CUDA(cudaGetLastError());
+        }
         if (!could_fail) n_groups_bound += n;  // upper bound without a device round trip
         else n_groups_bound = n_groups;
         rows_consumed += n;
+    }
+    ConsumeArgs generic_args(const std::vector<const void*>& data, const std::vector<const uint8_t*>& valid, const uint32_t* index_list, int64_t rows) {
+        ConsumeArgs a{};
+        a.key_data = data[0]; a.key_valid = valid[0]; a.key_ctype = c_types[0]; a.dropna = dropna ? 1 : 0;
+        a.n_rows = rows; a.index_list = index_list; a.tkeys = d_keys.as<long long>(); a.cap = cap;
+        a.counters = d_counters.as<long long>(); a.group_limit = (long long)(cap / 2); a.fail_list = d_fail.as<uint32_t>(); a.n_ops = n_funcs;
+        // rank-major sequence numbers: rows of a lower rank come first (the reference's row-block distribution), then row order
+        a.seq_base = ((unsigned long long)rank << 44) + (unsigned long long)rows_consumed;
+        for (int j = 0; j < n_funcs; j++) {
+            const FuncSpec& f = funcs[j];
+            a.ops[j].kind = f.kind; a.ops[j].in_ctype = f.in_ctype;
+            a.ops[j].in_data = f.in_col >= 0 ? data[f.in_col] : nullptr;
+            a.ops[j].in_valid = f.in_col >= 0 ? valid[f.in_col] : nullptr;
+            a.ops[j].a0 = d_a0[j].p; a.ops[j].a1 = f.has_a1 ? d_a1[j].p : nullptr;
+        }
+        return a;
     }
 
     int64_t n_groups_bound = 0;  // upper bound on groups in the table known to the host
@@ -2691,6 +2815,10 @@ class GroupbyState {
                 if (nk > 1) { c.row_words = nk + 1 + acc_count(); MkArgs m = mk_table_args(); m.group_limit = -1; xchg_combine_mk_kernel<<<grid_for(nf), 256, 0, stream>>>(m, c, nullptr, n_pes, 0); }
                 else
                 combine_partials_kernel<<<grid_for(nf), 256, 0, stream>>>(c);
+                if (has_firstlast) {  // over the whole slab again (idempotent): the table moved when it grew
+                    CombineArgs cf = combine_args((const unsigned long long*)((const char*)xchg_slab + XCHG_HDR_BYTES), 0, -1);
+                    combine_firstlast_fix_kernel<<<grid_for(1 << 20), 256, 0, stream>>>(cf, (const unsigned long long*)xchg_slab, n_pes, xchg_cap_rows);
+                }
                 launches++;
                 B200_CUDA(cudaGetLastError());
                 B200_CUDA(cudaStreamSynchronize(stream));
@@ -2719,6 +2847,7 @@ class GroupbyState {
     // ---- fused exchange (see xchg_pack_remote_kernel) ----
     bool xchg_fused = false;
     const void* xchg_slab = nullptr;
+    long long xchg_cap_rows = 0;
     DevBuf d_xchg_cursors;
     CombineArgs combine_args(const unsigned long long* in, int64_t n_rows, long long group_limit) {
         CombineArgs c{};
@@ -2770,10 +2899,11 @@ class GroupbyState {
         if (nk > 1) { c.row_words = nk + 1 + acc_count(); xchg_combine_mk_kernel<<<grid_for(std::min<int64_t>(cap_rows, 1 << 22)), 256, 0, stream>>>(mk_table_args(), c, (const unsigned long long*)my_slab, n_pes, cap_rows); }
         else
         xchg_combine_slab_kernel<<<grid_for(std::min<int64_t>(cap_rows, 1 << 22)), 256, 0, stream>>>(c, (const unsigned long long*)my_slab, n_pes, cap_rows);
+        if (has_firstlast) { combine_firstlast_fix_kernel<<<grid_for(std::min<int64_t>(cap_rows, 1 << 22)), 256, 0, stream>>>(c, (const unsigned long long*)my_slab, n_pes, cap_rows); launches++; }
         launches++;
         B200_CUDA(cudaGetLastError());
         xchg_fused = true;
-        xchg_slab = my_slab;
+        xchg_slab = my_slab; xchg_cap_rows = cap_rows;
         untracked_groups = 0;
     }
 
@@ -2824,7 +2954,7 @@ class GroupbyState {
         // the table now only has to hold the groups this rank owns: clear it for the combine step
         B200_CUDA(cudaStreamSynchronize(stream));  // offs is a stack buffer
         fill(d_keys.p, cap + 2, (unsigned long long)EMPTY_KEY);
-        for (int j = 0; j < n_funcs; j++) { fill(d_a0[j].p, cap + 2, funcs[j].init0); if (funcs[j].has_a1) fill(d_a1[j].p, cap + 2, 0); }
+        for (int j = 0; j < n_funcs; j++) { fill(d_a0[j].p, cap + 2, funcs[j].init0); if (funcs[j].has_a1) fill(d_a1[j].p, cap + 2, funcs[j].init1); }
         B200_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(long long), stream));
         n_groups = 0; n_groups_bound = 0; untracked_groups = 0;
     }
@@ -2848,6 +2978,12 @@ class GroupbyState {
         };
         launch(nullptr, n_rows);
         settle(n_rows, could_fail, launch);
+        if (has_firstlast) {
+            CombineArgs c = combine_args((const unsigned long long*)recv, n_rows, -1);
+            combine_firstlast_fix_kernel<<<grid_for(n_rows), 256, 0, stream>>>(c, nullptr, 0, 0);
+            launches++;
+            B200_CUDA(cudaGetLastError());
+        }
         if (!could_fail) { n_groups_bound += n_rows; untracked_groups += n_rows; } else n_groups_bound = n_groups + untracked_groups;
     }
 

@@ -21,7 +21,7 @@ from .._lib import ffi
 from ..table import CTable, Table, table_from_ctable
 
 # names must match supported_agg_funcs positions / Bodo_FTypes (groupby/_groupby_ftypes.h:17-110)
-FTYPES = {"size": 4, "sum": 6, "count": 7, "mean": 14, "min": 15, "max": 16, "var_pop": 22, "std_pop": 23, "var": 24, "std": 25, "skew": 27}
+FTYPES = {"size": 4, "sum": 6, "count": 7, "mean": 14, "min": 15, "max": 16, "first": 18, "last": 19, "var_pop": 22, "std_pop": 23, "var": 24, "std": 25, "skew": 27}
 
 
 class GroupbyState:

@@ -458,3 +458,32 @@ def test_generic_sm_partitioned_path_multi_pass(gpu_lib, n_groups, nullable):
         exp[f"o{j}"] = (g.size()["size"] if f == "size" else g.agg(x=("v", f))["x"]).values
     assert used >= 1
     assert_frames_equal(positional(got), positional(exp))
+
+
+@pytest.mark.parametrize("to_device", [False, True])
+@pytest.mark.parametrize("dropna", [True, False])
+def test_first_last_in_row_order_vs_pandas(gpu_lib, to_device, dropna):
+    """first / last = the first / last non-NA value of the group in ROW order (aggfunc<first / last>,
+    bodo/libs/groupby/_groupby_agg_funcs.h:594-611), across batch boundaries and table growth; a group without a non-NA value
+    gives NA; float NaN counts as NA."""
+    rng = np.random.default_rng(3)
+    n, ng = 300_007, 40_000
+    df = pd.DataFrame({
+        "k": pd.array(rng.integers(0, ng, n), dtype="Int64").copy(),
+        "i": pd.array(rng.integers(-(1 << 50), 1 << 50, n), dtype="Int64"),
+        "f": rng.random(n),
+        "s": rng.integers(-1000, 1000, n).astype(np.int32),
+    })
+    df.loc[rng.random(n) < 0.02, "k"] = pd.NA
+    df.loc[rng.random(n) < 0.3, "i"] = pd.NA
+    df.loc[rng.random(n) < 0.3, "f"] = np.nan
+    df.loc[df.k == 5, "i"] = pd.NA   # a group whose values are all NA
+    t = Table.from_pandas(df)
+    fn = ("first", "last", "first", "last", "first", "last", "size")
+    got = stream_groupby(t, (0,), fn, (0, 1, 2, 3, 4, 5, 6, 6), (1, 1, 2, 2, 3, 3), batch_size=70_001, to_device=to_device, dropna=dropna)
+    g = df.groupby("k", as_index=False, dropna=dropna)
+    exp = g.size()[["k"]]
+    for j, (c, f) in enumerate(zip(("i", "i", "f", "f", "s", "s"), fn)):
+        exp[f"o{j}"] = g.agg(x=(c, f))["x"].values
+    exp["o6"] = g.size()["size"].values
+    assert_frames_equal(positional(got), positional(exp))

@@ -43,13 +43,17 @@ def _worker(rank, world, port, q):
         # --- sharded groupby: consume local rows in 3 batches, exchange on the last one.  Twice: the fused exchange (pack kernel
         # storing into the owners' slabs over NVLink), then with a slab too small for the partial rows, which must fall back to
         # the NCCL all-to-all-v without losing or double counting anything ---
-        fn = ("sum", "count", "mean", "min", "max", "var")
+        fn = ("sum", "count", "mean", "min", "max", "var", "first", "last")
         nloc = hi - lo
         cuts = [0, nloc // 3, 2 * nloc // 3, nloc]
         host = Table.from_pandas(df)
         exp = O.groupby(k, None, list(fn[:5]), [v, v, vf, v, vf], n_pes=world, rank=rank)
         e = pd.DataFrame({"k": exp["keys"], **{f"f{j}": c[0] for j, c in enumerate(exp["cols"])}}).sort_values("k").reset_index(drop=True)
         e["f5"] = pd.DataFrame({"k": k, "vf": vf}).groupby("k").vf.var().reindex(e.k.to_numpy()).to_numpy()  # composite function through the exchange
+        # first / last in GLOBAL row order (rank-major: rank r holds rows [r * chunk, (r + 1) * chunk)), carried through the exchange
+        gv = pd.DataFrame({"k": k, "v": v}).groupby("k").v
+        e["f6"] = gv.first().reindex(e.k.to_numpy()).to_numpy()
+        e["f7"] = gv.last().reindex(e.k.to_numpy()).to_numpy()
         ok_keys = ok_int = ok_flt = True
         paths = []
         from bodo_b200.streaming import exchange as X
@@ -57,7 +61,7 @@ def _worker(rank, world, port, q):
             if slab_bytes is not None:
                 os.environ["B200_XCHG_SLAB_BYTES"] = str(slab_bytes)
                 X._CACHE.clear()
-            st = init_groupby_state(-1, (0,), fn, (0, 1, 2, 3, 4, 5, 6), (1, 1, 2, 1, 2, 2), parallel=True, expected_groups=64, device=rank,
+            st = init_groupby_state(-1, (0,), fn, (0, 1, 2, 3, 4, 5, 6, 7, 8), (1, 1, 2, 1, 2, 2, 1, 1), parallel=True, expected_groups=64, device=rank,
                                     output_batch_size=1 << 30)
             for b in range(3):
                 groupby_build_consume_batch(st, table_to_device(host.slice(cuts[b], cuts[b + 1]), rank), b == 2, True)
@@ -65,11 +69,11 @@ def _worker(rank, world, port, q):
             got = out.to_pandas()
             paths.append(st.exchange_path)
             delete_groupby_state(st)
-            got.columns = ["k"] + [f"f{j}" for j in range(6)]
+            got.columns = ["k"] + [f"f{j}" for j in range(8)]
             g = got.sort_values("k").reset_index(drop=True)
             okk = bool(len(g) == len(e) and (g.k.to_numpy() == e.k.to_numpy()).all())
             ok_keys = ok_keys and okk
-            ok_int = ok_int and okk and all((g[c].to_numpy() == e[c].to_numpy()).all() for c in ("f0", "f1", "f3"))
+            ok_int = ok_int and okk and all((g[c].to_numpy() == e[c].to_numpy()).all() for c in ("f0", "f1", "f3", "f6", "f7"))
             ok_flt = ok_flt and okk and all(np.allclose(g[c].to_numpy(dtype=float), e[c].to_numpy(dtype=float), rtol=1e-5, atol=1e-8) for c in ("f2", "f4", "f5"))
         os.environ.pop("B200_XCHG_SLAB_BYTES", None)
         X._CACHE.clear()
