@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
+#include <memory>
 #include <vector>
 
 #include "common.cuh"
@@ -32,6 +33,7 @@ enum OpKind : int { K_SUM_I64 = 0, K_SUM_F64, K_COUNT, K_SIZE, K_MEAN, K_MIN_I64
                     // first / last non-NA value in row order (aggfunc<first / last>, _groupby_agg_funcs.h:594-611): a0 = value
                     // bits, a1 = sequence number of the row that supplied it (see groupby_firstlast_fix_kernel)
                     K_FIRST, K_LAST,
+                    K_NUNIQUE,  // number of distinct non-NA values: filled at finalize from a nested (key, value) distinct state
                     // evaluation-only kinds of composite functions (accumulators: a K_MEAN pair + K_SUMSQ (+ K_SUMCUBE))
                     E_VAR, E_STD, E_VAR_POP, E_STD_POP, E_SKEW };
 
@@ -401,7 +403,7 @@ __global__ void eval_output_kernel(const __grid_constant__ EvalArgs a) {
             bool valid = in;
             if (in) {
                 switch (op.kind) {
-                    case K_SUM_I64: case K_COUNT: case K_SIZE:
+                    case K_SUM_I64: case K_COUNT: case K_SIZE: case K_NUNIQUE:
                         store_int_typed(op.out_data, op.out_ctype, p, ((const long long*)op.a0)[s]);
                         break;
                     case K_SUM_F64:
@@ -543,7 +545,7 @@ __device__ __forceinline__ void combine_apply(const CombineArgs& a, uint64_t slo
             unsigned long long v0 = r[w++];
             unsigned long long v1 = a.a1[j] ? r[w++] : 0;
             switch (a.kinds[j]) {
-                case K_SUM_I64: case K_COUNT: case K_SIZE: atomicAdd((unsigned long long*)a.a0[j] + slot, v0); break;
+                case K_SUM_I64: case K_COUNT: case K_SIZE: case K_NUNIQUE: atomicAdd((unsigned long long*)a.a0[j] + slot, v0); break;
                 case K_SUM_F64: case K_SUMSQ_F64: case K_SUMCUBE_F64: atomicAdd((double*)a.a0[j] + slot, __longlong_as_double((long long)v0)); break;
                 case K_MEAN:
                     atomicAdd((double*)a.a0[j] + slot, __longlong_as_double((long long)v0));
@@ -807,6 +809,8 @@ __global__ void rehash_mk_kernel(const __grid_constant__ RehashMkArgs a) {
 // widened int64 values the table stores.
 struct MkOwner {
     int nk, n_pes, rank;
+    int own_nk;  // 0: ownership by the hash of all key columns (the reference's hash_keys); 1: by the FIRST key column alone, hashed
+                 // like a single-key state's key (nunique's nested (key, value) state: a key's pairs live where the key lives)
     const long long* mk[MAX_KEYS];
     const unsigned char* mkmask;
     int key_ctype[MAX_KEYS];
@@ -822,6 +826,31 @@ __device__ __forceinline__ uint32_t mk_ref_hash(const long long* keys, unsigned 
     }
     return h;
 }
+__device__ __forceinline__ uint32_t mk_owner_hash(const MkOwner& ow, const long long* keys, unsigned int mask) {
+    if (ow.own_nk == 1) return (mask & 1u) ? (uint32_t)key_hash(keys[0]) : (uint32_t)xxh3_64_short(1ull, 8, SEED_HASH_PARTITION);
+    return mk_ref_hash(keys, mask, ow.nk, ow.key_ctype);
+}
+// nunique: one thread per distinct (key, value) pair of the nested state; pairs whose value is NA do not count
+struct NuniqueArgs {
+    const long long* pk; const long long* pv; const unsigned char* pmask; const uint64_t* slot_of_out; long long n_pairs;
+    long long* tkeys; uint64_t cap; long long* counters; int dropna;
+    int n_acc; unsigned long long* acc[MAX_OPS];
+};
+__global__ void nunique_count_kernel(const __grid_constant__ NuniqueArgs a) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < a.n_pairs; p += (long long)gridDim.x * blockDim.x) {
+        const uint64_t s = a.slot_of_out[p];
+        const unsigned int m = a.pmask[s];
+        if (!(m & 2u)) continue;  // NA value
+        uint64_t slot;
+        if (!(m & 1u)) { if (a.dropna) continue; slot = a.cap; a.counters[3] = 1; }
+        else {
+            const long long key = a.pk[s];
+            if (key == EMPTY_KEY) { slot = a.cap + 1; a.counters[4] = 1; }
+            else { slot = find_only(a.tkeys, a.cap, key); if (slot == ~0ull) continue; }  // (every key of a pair is a group of the outer table)
+        }
+        for (int j = 0; j < a.n_acc; j++) atomicAdd(a.acc[j] + slot, 1ull);
+    }
+}
 __global__ void compact_mk_kernel(const unsigned long long* __restrict__ tags, uint64_t cap, long long* cursor, uint64_t* slot_of_out,
                                   const __grid_constant__ MkOwner ow) {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -830,7 +859,7 @@ __global__ void compact_mk_kernel(const unsigned long long* __restrict__ tags, u
         if (occ && ow.n_pes > 1) {  // only the groups this rank owns (see compact_slots_kernel)
             long long keys[MAX_KEYS];
             for (int j = 0; j < ow.nk; j++) keys[j] = ow.mk[j][s0];
-            occ = hash_to_rank_u32(mk_ref_hash(keys, ow.mkmask[s0], ow.nk, ow.key_ctype), ow.n_pes) == ow.rank;
+            occ = hash_to_rank_u32(mk_owner_hash(ow, keys, ow.mkmask[s0]), ow.n_pes) == ow.rank;
         }
         unsigned m = __ballot_sync(0xffffffffu, occ);
         int lane = threadIdx.x & 31;
@@ -863,7 +892,7 @@ __global__ void xchg_pack_remote_mk_kernel(const __grid_constant__ XchgPackMkArg
         if (occ) {
             for (int j = 0; j < a.ow.nk; j++) keys[j] = a.ow.mk[j][s];
             mask = a.ow.mkmask[s];
-            d = hash_to_rank_u32(mk_ref_hash(keys, mask, a.ow.nk, a.ow.key_ctype), a.ow.n_pes);
+            d = hash_to_rank_u32(mk_owner_hash(a.ow, keys, mask), a.ow.n_pes);
             if (d == a.ow.rank) d = -1;
         }
         const unsigned peers = __match_any_sync(0xffffffffu, d);
@@ -1751,6 +1780,11 @@ class GroupbyState {
     std::vector<OutSpec> outs;
     bool dropna, parallel;
     bool has_firstlast = false;
+    int owner_nk = 0;  // see MkOwner::own_nk
+    // nunique: one nested distinct state over (key, value) per value column; `prims` = the K_NUNIQUE accumulators it feeds
+    struct NuInner { int in_col; std::unique_ptr<GroupbyState> st; std::vector<int> prims; };
+    std::vector<NuInner> nu_inner;
+    bool nu_applied = false;
     int n_pes, rank;
     int64_t output_batch_size;
     int sms;
@@ -1853,6 +1887,17 @@ class GroupbyState {
                     else f.init0 = mn ? (unsigned long long)INT64_MAX : (unsigned long long)INT64_MIN;
                     break;
                 }
+                case FT_NUNIQUE: {
+                    // nunique_computation (bodo/libs/groupby/_groupby_col_set.cpp:1771-1810): distinct non-NA values per group
+                    B200_REQUIRE(nk == 1, "b200 groupby: nunique is supported for single-column keys");
+                    B200_REQUIRE(!isf, "b200 groupby: nunique of a float column is not supported (integer / date / bool value columns)");
+                    f.kind = K_NUNIQUE; f.out_ctype = CT_INT64; f.out_arrtype = ARR_NUMPY;
+                    size_t q = 0;
+                    while (q < nu_inner.size() && nu_inner[q].in_col != f.in_col) q++;
+                    if (q == nu_inner.size()) { nu_inner.emplace_back(); nu_inner[q].in_col = f.in_col; }
+                    nu_inner[q].prims.push_back((int)funcs.size());
+                    break;
+                }
                 case FT_FIRST: case FT_LAST:
                     B200_REQUIRE(nk == 1, "b200 groupby: first / last are supported for single-column keys");
                     f.kind = f.ftype == FT_FIRST ? K_FIRST : K_LAST;
@@ -1883,7 +1928,7 @@ class GroupbyState {
                 }
                 default:
                     throw Error("b200 groupby: unsupported aggregate function ftype=" + std::to_string(f.ftype) +
-                                " (supported: size, sum, count, mean, min, max, first, last, var, std, var_pop, std_pop, skew)");
+                                " (supported: size, sum, count, nunique, mean, min, max, first, last, var, std, var_pop, std_pop, skew)");
             }
             OutSpec o{};
             o.ftype = f.ftype; o.kind = f.kind; o.prim[0] = (int)funcs.size(); o.n_prim = 1; o.out_ctype = f.out_ctype; o.out_arrtype = f.out_arrtype;
@@ -1905,6 +1950,13 @@ class GroupbyState {
         alloc_table(want, d_keys, d_a0, d_a1);
         if (nk > 1) alloc_mk(want, d_tags, d_mk, d_mkmask);
         cap = want;
+        for (auto& ni : nu_inner) {  // nested distinct states over (key, value); their groups are owned where the KEY is owned
+            const int8_t ict[2] = {c_types[0], c_types[ni.in_col]}, iat[2] = {arr_types[0], arr_types[ni.in_col]};
+            const int32_t no_off[1] = {0};
+            ni.st.reset(new GroupbyState(ict, iat, 2, nullptr, no_off, nullptr, 0, 2, 1ll << 40, parallel, /*dropna=*/false, device, n_pes, rank,
+                                         expected_groups > 0 ? expected_groups * 4 : 0, stream));
+            ni.st->owner_nk = 1;
+        }
         t_ctor = now() - t0;
     }
 
@@ -2626,6 +2678,13 @@ class GroupbyState {
             B200_REQUIRE(t->cols[c].c_type == c_types[c], "b200 groupby: batch column dtype differs from the build schema");
             B200_REQUIRE(n == 0 || t->cols[c].data != nullptr, "b200 groupby: null data pointer");
         }
+        for (auto& ni : nu_inner) {  // nunique: the (key, value) pairs of this batch go to the nested distinct state
+            b200_column pc[2] = {t->cols[0], t->cols[ni.in_col]};
+            b200_table pt{};
+            pt.n_cols = 2; pt.n_rows = n; pt.cols = pc; pt.device = t->device;
+            ni.st->consume(&pt);
+            B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
+        }
         if (coalesce(t, n)) return;  // small batch of the fast-path signature: buffered until a launch is worth it
         flush_coalesced();
         if (t->device >= 0) {
@@ -2748,12 +2807,38 @@ class GroupbyState {
         n_out = -1;  // known on the device (counters[2]); the host learns it with the next counter read-back
     }
 
+    // nunique: count the distinct (key, value) pairs of every nested state into the outer table.  On the sharded path the host
+    // has exchanged the nested states first (their pairs are owned where the key is owned) and the outer table already holds
+    // the groups this rank owns.
+    void apply_nunique() {
+        if (nu_applied || nu_inner.empty()) return;
+        for (auto& ni : nu_inner) {
+            GroupbyState& in = *ni.st;
+            B200_REQUIRE(!(parallel && n_pes > 1) || in.xchg_fused, "b200 groupby: nunique on the sharded path: exchange the nested states (b200_groupby_inner_state) before the outer finalize");
+            const int64_t n_pairs = in.finalize();
+            B200_REQUIRE(n_pairs >= 0, "b200 groupby: nunique: the nested exchange overflowed its slab");
+            B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
+            if (n_pairs == 0) continue;
+            NuniqueArgs a{};
+            a.pk = in.d_mk[0].as<long long>(); a.pv = in.d_mk[1].as<long long>(); a.pmask = in.d_mkmask.as<unsigned char>();
+            a.slot_of_out = in.d_slot_of_out.as<uint64_t>(); a.n_pairs = n_pairs;
+            a.tkeys = d_keys.as<long long>(); a.cap = cap; a.counters = d_counters.as<long long>(); a.dropna = dropna ? 1 : 0;
+            a.n_acc = (int)ni.prims.size();
+            for (int j = 0; j < a.n_acc; j++) a.acc[j] = d_a0[ni.prims[j]].as<unsigned long long>();
+            nunique_count_kernel<<<grid_for(n_pairs), 256, 0, stream>>>(a);
+            launches++;
+            B200_CUDA(cudaGetLastError());
+        }
+        nu_applied = true;
+    }
+
     int64_t finalize() {
         if (finalized) return n_out;
         double tf0 = now();
         struct Acc3 { double& t; double t0; ~Acc3() { t += now() - t0; } } acc3{t_finalize, tf0};
         B200_CUDA(cudaSetDevice(device)); scratch_set_stream(stream);
         flush_coalesced();
+        apply_nunique();
         compact(/*owned_only=*/parallel && n_pes > 1);
         const int64_t max_out = max_out_bound();
         EvalArgs e{};
@@ -2833,7 +2918,7 @@ class GroupbyState {
 
     MkOwner mk_owner(bool owned_only) {
         MkOwner o{};
-        o.nk = nk; o.n_pes = owned_only ? n_pes : 1; o.rank = rank; o.mkmask = d_mkmask.as<unsigned char>();
+        o.nk = nk; o.n_pes = owned_only ? n_pes : 1; o.rank = rank; o.mkmask = d_mkmask.as<unsigned char>(); o.own_nk = owner_nk;
         for (int j = 0; j < nk; j++) { o.mk[j] = d_mk[j].as<long long>(); o.key_ctype[j] = c_types[j]; }
         return o;
     }
@@ -3096,6 +3181,13 @@ int b200_groupby_shuffle_combine(void* state, const void* recv_buf, int64_t n_re
     return 0;
     B200_CATCH(-1)
 }
+int32_t b200_groupby_num_inner_states(void* state) { return state ? (int32_t)((GroupbyState*)state)->nu_inner.size() : 0; }
+void* b200_groupby_inner_state(void* state, int32_t i) {
+    auto* s = (GroupbyState*)state;
+    if (!s || i < 0 || i >= (int32_t)s->nu_inner.size()) { b200::set_last_error("b200_groupby_inner_state: bad arguments"); return nullptr; }
+    return s->nu_inner[i].st.get();
+}
+
 int64_t b200_groupby_finalize(void* state) {
     B200_TRY
     return ((GroupbyState*)state)->finalize();

@@ -21,7 +21,7 @@ from .._lib import ffi
 from ..table import CTable, Table, table_from_ctable
 
 # names must match supported_agg_funcs positions / Bodo_FTypes (groupby/_groupby_ftypes.h:17-110)
-FTYPES = {"size": 4, "sum": 6, "count": 7, "mean": 14, "min": 15, "max": 16, "first": 18, "last": 19, "var_pop": 22, "std_pop": 23, "var": 24, "std": 25, "skew": 27}
+FTYPES = {"size": 4, "sum": 6, "count": 7, "nunique": 8, "mean": 14, "min": 15, "max": 16, "first": 18, "last": 19, "var_pop": 22, "std_pop": 23, "var": 24, "std": 25, "skew": 27}
 
 
 class GroupbyState:
@@ -121,6 +121,22 @@ class GroupbyState:
         t0 = time.perf_counter()
         slabs = X.get_slabs(self.process_group, self.device)
         done = False
+        # nunique: the nested (key, value) distinct states are exchanged first (fused form only: their partial rows are multi-key)
+        for i in range(int(L.b200_groupby_num_inner_states(h))):
+            hi = _lib.check_ptr(L.b200_groupby_inner_state(h, i), "groupby nunique")
+            if slabs is None:
+                raise _lib.B200Error("groupby nunique on the sharded path needs the fused exchange (torch symmetric memory)")
+            row_bytes = int(L.b200_groupby_exchange_row_bytes(hi))
+            cap_rows = (slabs.slab_bytes - X.HDR_BYTES) // (self.n_pes * row_bytes)
+            peers_dev, my_slab, hdl = slabs.next()
+            stream = torch.cuda.ExternalStream(self.stream) if self.stream else torch.cuda.default_stream(self.device)
+            with torch.cuda.stream(stream):
+                _lib.check(L.b200_groupby_exchange_fused_pack(hi, ffi.cast("void* const*", peers_dev), cap_rows), "groupby nunique exchange (pack)")
+                hdl.barrier(channel=0)
+                _lib.check(L.b200_groupby_exchange_fused_combine(hi, ffi.cast("void*", my_slab), cap_rows), "groupby nunique exchange (combine)")
+            if int(L.b200_groupby_finalize(hi)) < 0:
+                raise _lib.B200Error("groupby nunique: the distinct (key, value) pairs did not fit the exchange slab "
+                                     "(raise B200_XCHG_SLAB_BYTES)")
         if slabs is not None:
             row_bytes = int(L.b200_groupby_exchange_row_bytes(h))
             cap_rows = (slabs.slab_bytes - X.HDR_BYTES) // (self.n_pes * row_bytes)

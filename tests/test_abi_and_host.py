@@ -96,7 +96,7 @@ def test_table_from_arrow_zero_copy():
 def test_unsupported_inputs_fail_loudly():
     from bodo_b200.streaming.groupby import init_groupby_state
     with pytest.raises(B200Error, match="unsupported aggregate function"):
-        init_groupby_state(-1, (0,), ("nunique",), (0, 1), (1,))
+        init_groupby_state(-1, (0,), ("median",), (0, 1), (1,))
     with pytest.raises(B200Error, match="min_row_number_filter"):
         init_groupby_state(-1, (0,), ("sum",), (0, 1), (1,), mrnf_sort_col_inds=(1,))
     with pytest.raises(TypeError, match="object dtype|unsupported"):

@@ -487,3 +487,32 @@ def test_first_last_in_row_order_vs_pandas(gpu_lib, to_device, dropna):
         exp[f"o{j}"] = g.agg(x=(c, f))["x"].values
     exp["o6"] = g.size()["size"].values
     assert_frames_equal(positional(got), positional(exp))
+
+
+@pytest.mark.parametrize("to_device", [False, True])
+@pytest.mark.parametrize("dropna", [True, False])
+def test_nunique_vs_pandas(gpu_lib, to_device, dropna):
+    """nunique = distinct non-NA values per group (nunique_computation, bodo/libs/groupby/_groupby_col_set.cpp:1771-1810), mixed
+    with other aggregates, over nullable and plain columns, across batches; the reference's GPU matrix lists it
+    (bodo/tests/test_df_lib/test_gpu/test_gpu_end_to_end.py:68-110)."""
+    rng = np.random.default_rng(12)
+    n, ng = 250_003, 9_000
+    df = pd.DataFrame({
+        "k": pd.array(rng.integers(0, ng, n), dtype="Int64"),
+        "a": pd.array(rng.integers(0, 40, n), dtype="Int64"),
+        "b": rng.integers(-5, 5, n).astype(np.int32),
+    })
+    df.loc[rng.random(n) < 0.02, "k"] = pd.NA
+    df.loc[rng.random(n) < 0.2, "a"] = pd.NA
+    df.loc[df.k == 7, "a"] = pd.NA  # a group without a non-NA value: nunique 0
+    t = Table.from_pandas(df)
+    fn = ("nunique", "sum", "nunique", "size", "nunique")
+    got = stream_groupby(t, (0,), fn, (0, 1, 2, 3, 3, 4), (1, 1, 2, 1), batch_size=60_001, to_device=to_device, dropna=dropna)
+    g = df.groupby("k", as_index=False, dropna=dropna)
+    exp = g.size()[["k"]]
+    exp["o0"] = g.agg(x=("a", "nunique"))["x"].values
+    exp["o1"] = g.agg(x=("a", "sum"))["x"].values
+    exp["o2"] = g.agg(x=("b", "nunique"))["x"].values
+    exp["o3"] = g.size()["size"].values
+    exp["o4"] = exp["o0"]
+    assert_frames_equal(positional(got), positional(exp))
