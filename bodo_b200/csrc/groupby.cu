@@ -3217,6 +3217,7 @@ int64_t b200_groupby_get_metric(void* state, int32_t which) {
         case 10: return s->lc_launches;
         case 11: return s->co_batches;
         case 12: return s->spgg_launches;
+        case 13: { cudaSetDevice(s->device); s->read_counters(); return s->n_groups + s->untracked_groups; }  // exact (synchronises the stream)
         case 100: s->profiling = true; return 0;
         default: return -1;
     }

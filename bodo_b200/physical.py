@@ -147,7 +147,7 @@ class PhysicalFilterProject:
         import torch
 
         from . import _lib
-        from .streaming.dist_join import to_device
+        from .table import to_device
         from .table import ArrTypes, Column, CTable, np_dtype_of
 
         dev_i = self.device if self.device is not None else (batch.device if batch.device >= 0 else torch.cuda.current_device())
@@ -196,7 +196,7 @@ class PhysicalReadArrowDevice:
         self.cur = 0
 
     def ProduceBatch(self):
-        from .streaming.dist_join import to_device
+        from .table import to_device
 
         n = self.arrow.num_rows
         sl = self.arrow.slice(self.cur, self.batch_size)

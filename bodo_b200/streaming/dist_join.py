@@ -29,7 +29,7 @@ import numpy as np
 
 from .. import _lib
 from ..shuffle import exchange_table, partition_device, with_schema_validity
-from ..table import ArrTypes, Column, Table, np_dtype_of
+from ..table import ArrTypes, Column, Table, np_dtype_of, to_device  # noqa: F401 (to_device is re-exported)
 from . import join as J
 
 
@@ -39,25 +39,6 @@ def bcast_join_threshold() -> int:
     if v < 0:
         raise _lib.B200Error("hash_join: bcast_join_threshold < 0")
     return v
-
-
-def to_device(table: Table, device: int) -> Table:
-    """Host batch -> device batch (torch tensors); device batches pass through."""
-    import torch
-
-    if table.device >= 0:
-        return table
-    dev = torch.device("cuda", device)
-    cols = []
-    for c in table.columns:
-        d = torch.from_numpy(np.ascontiguousarray(c.data)).to(dev, non_blocking=False)
-        v = None
-        if c.validity is not None:
-            vb = np.zeros((len(c.validity) + 7) // 8 * 8 + 8, dtype=np.uint8)
-            vb[: len(c.validity)] = c.validity
-            v = torch.from_numpy(vb).to(dev)
-        cols.append(Column(d, v, c.c_type, c.arr_type, c.length))
-    return Table(cols, list(table.names))
 
 
 def _as_tensor(x, dev):

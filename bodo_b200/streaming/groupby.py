@@ -101,6 +101,51 @@ class GroupbyState:
             uniq.append(cand)
         self.out_names = key_names + uniq
 
+    # ---- reduce-or-shuffle (reference: GroupbyIncrementalShuffleState::ShouldShuffleAfterProcessing,
+    # bodo/libs/streaming/_groupby.cpp:1655-1711: an HLL estimate of how many NEW groups the pending rows hold decides whether they are
+    # pre-reduced locally or shuffled as they are; threshold agg_reduction_threshold = 0.85, :1556) ----
+    # Here every batch is aggregated into the local table first (that is the fast kernel), so the uniqueness is measured, not
+    # estimated: groups in the tables / rows consumed, summed over the ranks.  While it stays below the threshold the ranks keep
+    # pre-aggregating and exchange PARTIAL AGGREGATES once, at the end.  Above it (groups ~ rows: pre-aggregation buys nothing, the
+    # table of every rank would grow towards its share of ALL rows and the one final exchange would move them all at once) the
+    # state switches to the raw-row form: every further batch is hash-partitioned (b200_shuffle_partition) and exchanged right away
+    # (all-to-all-v), each rank aggregates only rows of groups it owns, and the final exchange only carries what was aggregated
+    # before the switch.  Collective: decided once, from the first >= B200_SHUFFLE_DECISION_ROWS rows, identically on every rank.
+    raw_row_mode = False
+    shuffle_decided = False
+    raw_rows_shuffled = 0
+
+    def _decide_reduce_or_shuffle(self):
+        import os
+
+        import torch
+        import torch.distributed as dist
+
+        L = _lib.lib()
+        dev = torch.device("cuda", self.device)
+        t = torch.tensor([int(L.b200_groupby_get_metric(self.handle, 13)), int(L.b200_groupby_get_metric(self.handle, 2))], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, group=self.process_group)
+        groups, rows = (int(x) for x in t.tolist())
+        if rows < int(os.environ.get("B200_SHUFFLE_DECISION_ROWS", 1 << 22)):
+            return
+        thr = min(1.0, max(0.0, float(os.environ.get("BODO_STREAM_GROUPBY_AGG_REDUCTION_THRESHOLD", os.environ.get("B200_AGG_REDUCTION_THRESHOLD", 0.85)))))
+        self.shuffle_decided = True
+        self.raw_row_mode = rows > 0 and groups / rows >= thr
+        self.local_uniqueness = groups / max(rows, 1)
+
+    def _shuffle_rows(self, phys: Table) -> Table:
+        import torch
+
+        from ..shuffle import shuffle_table
+        from ..table import to_device
+
+        dev_tab = to_device(phys, self.device)
+        stream = torch.cuda.ExternalStream(self.stream) if self.stream else torch.cuda.default_stream(self.device)
+        with torch.cuda.stream(stream):
+            out = shuffle_table(dev_tab, len(self.key_inds), True, group=self.process_group, stream=self.stream)
+        self.raw_rows_shuffled += phys.n_rows
+        return out
+
     def _exchange(self):
         """Hash-partition exchange of the partial aggregates after the last local batch, then finalize.
 
@@ -250,11 +295,16 @@ def groupby_build_consume_batch(groupby_state: GroupbyState, table: Table, is_la
     st._ensure(table)
     L = _lib.lib()
     phys = table.select(st.build_indices)
+    sharded = st.parallel and st.n_pes > 1
+    if sharded and st.raw_row_mode:
+        phys = st._shuffle_rows(phys)  # this rank's share of every rank's batch: all of its rows are owned here
     ct = CTable(phys)
     req = ffi.new("int32_t*")
     rc = _lib.check(L.b200_groupby_build_consume_batch(st.handle, ct.ptr, int(bool(is_last)), int(bool(is_final_pipeline)), req),
                     "groupby_build_consume_batch")
-    if is_last and st.parallel and st.n_pes > 1 and not st.exchanged:
+    if sharded and not is_last and not st.shuffle_decided:
+        st._decide_reduce_or_shuffle()
+    if is_last and sharded and not st.exchanged:
         st._exchange()
     return bool(rc), bool(req[0])
 

@@ -386,3 +386,22 @@ def table_from_ctable(ctab, n_cols: int, names: Sequence[str], owner: Any) -> Ta
             validity = DeviceArray(int(ffi.cast("uintptr_t", cc.validity)), (cc.length + 7) // 8, np.uint8, dev, owner)
         cols.append(Column(data, validity, cc.c_type, cc.arr_type, cc.length))
     return Table(cols, list(names))
+
+
+def to_device(table: Table, device: int) -> Table:
+    """Host batch -> device batch (torch tensors); device batches pass through."""
+    import torch
+
+    if table.device >= 0:
+        return table
+    dev = torch.device("cuda", device)
+    cols = []
+    for c in table.columns:
+        d = torch.from_numpy(np.ascontiguousarray(c.data)).to(dev, non_blocking=False)
+        v = None
+        if c.validity is not None:
+            vb = np.zeros((len(c.validity) + 7) // 8 * 8 + 8, dtype=np.uint8)
+            vb[: len(c.validity)] = c.validity
+            v = torch.from_numpy(vb).to(dev)
+        cols.append(Column(d, v, c.c_type, c.arr_type, c.length))
+    return Table(cols, list(table.names))

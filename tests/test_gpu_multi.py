@@ -114,6 +114,53 @@ def _worker(rank, world, port, q):
             _, dest2 = hash_keys_table(kt, 2, world)
             ok_mk = ok_mk and bool((dest2.cpu().numpy() == rank).all())
         ok_keys = ok_keys and ok_mk
+        # --- nunique on the sharded path: the nested distinct (key, value) states are exchanged first (pairs owned where the key
+        # is owned), then counted into the owned groups ---
+        dfu = pd.DataFrame({"k": k[lo:hi], "u": (v[lo:hi] % 7).astype(np.int64)})
+        st3 = init_groupby_state(-1, (0,), ("nunique", "count"), (0, 1, 2), (1, 1), parallel=True, device=rank, output_batch_size=1 << 30)
+        groupby_build_consume_batch(st3, table_to_device(Table.from_pandas(dfu.iloc[: nloc // 2]), rank), False, True)
+        groupby_build_consume_batch(st3, table_to_device(Table.from_pandas(dfu.iloc[nloc // 2:]), rank), True, True)
+        out3, _ = groupby_produce_output_batch(st3, True)
+        g3 = out3.to_pandas()
+        delete_groupby_state(st3)
+        g3.columns = ["k", "nu", "c"]
+        g3 = g3.sort_values("k").reset_index(drop=True)
+        gg = pd.DataFrame({"k": k, "u": v % 7}).groupby("k").u
+        owned = e.k.to_numpy()
+        ok_nu = bool(len(g3) == len(owned) and (g3.k.to_numpy() == owned).all()
+                     and (g3.nu.to_numpy() == gg.nunique().reindex(owned).to_numpy()).all()
+                     and (g3.c.to_numpy() == gg.count().reindex(owned).to_numpy()).all())
+        ok_keys = ok_keys and ok_nu
+        # --- reduce-or-shuffle: nearly unique keys make the ranks switch to the raw-row form (batches are hash-partitioned and
+        # exchanged as they come); few groups keep the partial-aggregate form.  Same result either way ---
+        os.environ["B200_SHUFFLE_DECISION_ROWS"] = "20000"
+        from bodo_b200.streaming.groupby import get_metric
+        modes = []
+        for uniq in (True, False):
+            rngu = np.random.default_rng(31)
+            nu_ = 240_000
+            ku = rngu.permutation(nu_).astype(np.int64) if uniq else rngu.integers(0, 300, nu_).astype(np.int64)
+            wu = rngu.integers(-9, 9, nu_).astype(np.int64)
+            cu = (nu_ + world - 1) // world
+            mine = pd.DataFrame({"k": ku[rank * cu:(rank + 1) * cu], "w": wu[rank * cu:(rank + 1) * cu]})
+            st4 = init_groupby_state(-1, (0,), ("sum", "count"), (0, 1, 2), (1, 1), parallel=True, device=rank, output_batch_size=1 << 30)
+            nb4 = 6
+            for b in range(nb4):
+                sl = mine.iloc[b * len(mine) // nb4:(b + 1) * len(mine) // nb4]
+                groupby_build_consume_batch(st4, Table.from_pandas(sl) if b % 2 else table_to_device(Table.from_pandas(sl), rank), b == nb4 - 1, True)
+            modes.append((st4.raw_row_mode, st4.raw_rows_shuffled > 0))
+            out4, _ = groupby_produce_output_batch(st4, True)
+            g4 = out4.to_pandas()
+            delete_groupby_state(st4)
+            g4.columns = ["k", "s", "c"]
+            allg4 = [None] * world
+            dist.all_gather_object(allg4, g4)
+            u4 = pd.concat(allg4, ignore_index=True).sort_values("k").reset_index(drop=True)
+            e4 = pd.DataFrame({"k": ku, "w": wu}).groupby("k", as_index=False).agg(s=("w", "sum"), c=("w", "count"))
+            ok_keys = ok_keys and bool(len(u4) == len(e4) and (u4.to_numpy() == e4.to_numpy()).all())
+            ok_keys = ok_keys and bool((O.hash_to_rank(g4.k.to_numpy(), None, world) == rank).all())
+        ok_keys = ok_keys and modes == [(True, True), (False, False)]
+        os.environ.pop("B200_SHUFFLE_DECISION_ROWS", None)
         # --- shuffle_table over NCCL: rows land on hash_to_rank(key), nothing lost ---
         sh = shuffle_table(t, 1, True)
         sdf = sh.to_pandas()
