@@ -134,6 +134,7 @@ def _worker(rank, world, port, q):
         # --- reduce-or-shuffle: nearly unique keys make the ranks switch to the raw-row form (batches are hash-partitioned and
         # exchanged as they come); few groups keep the partial-aggregate form.  Same result either way ---
         os.environ["B200_SHUFFLE_DECISION_ROWS"] = "20000"
+        os.environ["B200_COALESCE"] = "0"  # (small batches would sit in the coalescing buffer: nothing to measure yet)
         from bodo_b200.streaming.groupby import get_metric
         modes = []
         for uniq in (True, False):
@@ -157,10 +158,16 @@ def _worker(rank, world, port, q):
             dist.all_gather_object(allg4, g4)
             u4 = pd.concat(allg4, ignore_index=True).sort_values("k").reset_index(drop=True)
             e4 = pd.DataFrame({"k": ku, "w": wu}).groupby("k", as_index=False).agg(s=("w", "sum"), c=("w", "count"))
-            ok_keys = ok_keys and bool(len(u4) == len(e4) and (u4.to_numpy() == e4.to_numpy()).all())
-            ok_keys = ok_keys and bool((O.hash_to_rank(g4.k.to_numpy(), None, world) == rank).all())
+            ok_rs = bool(len(u4) == len(e4) and (u4.to_numpy() == e4.to_numpy()).all())
+            ok_place = bool((O.hash_to_rank(g4.k.to_numpy(), None, world) == rank).all())
+            if not (ok_rs and ok_place):
+                print(f"[rank {rank}] reduce-or-shuffle uniq={uniq}: result ok={ok_rs} placement ok={ok_place} rows {len(u4)} vs {len(e4)}", flush=True)
+            ok_keys = ok_keys and ok_rs and ok_place
+        if modes != [(True, True), (False, False)] or not ok_nu or not ok_mk:
+            print(f"[rank {rank}] modes={modes} ok_nu={ok_nu} ok_mk={ok_mk}", flush=True)
         ok_keys = ok_keys and modes == [(True, True), (False, False)]
         os.environ.pop("B200_SHUFFLE_DECISION_ROWS", None)
+        os.environ.pop("B200_COALESCE", None)
         # --- shuffle_table over NCCL: rows land on hash_to_rank(key), nothing lost ---
         sh = shuffle_table(t, 1, True)
         sdf = sh.to_pandas()
