@@ -1075,16 +1075,16 @@ constexpr int SPG_HOT_TAB = 8192;        // counting-table slots of the sample k
 constexpr size_t SPG_HOT_SAMPLE_SMEM = (size_t)SPG_HOT_TAB * 12 + SPG_HOT_SLOTS * 8;
 __device__ __forceinline__ unsigned int spg_hot_bucket(uint64_t h) { return (unsigned int)(h >> 8) & (SPG_HOT_BUCKETS - 1); }
 
-__global__ void __launch_bounds__(1024, 1) spg_hot_sample_kernel(const long long* keys, int64_t n_rows, long long* hot_tab, int* n_hot) {
+__global__ void __launch_bounds__(1024, 1) spg_hot_sample_kernel(const long long* keys, const long long* vals, int64_t n_rows, long long* hot_tab, int* n_hot) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     long long* tk = (long long*)smem_raw;                  // SPG_HOT_TAB keys
     unsigned int* tc = (unsigned int*)(tk + SPG_HOT_TAB);  // their sample counts
     long long* hk = (long long*)(tc + SPG_HOT_TAB);        // SPG_HOT_SLOTS: the hot table being built
-    __shared__ unsigned int fill, nh;
+    __shared__ unsigned int fill, nh, nwide;
     const int tid = threadIdx.x;
     for (int s = tid; s < SPG_HOT_TAB; s += 1024) { tk[s] = EMPTY_KEY; tc[s] = 0; }
     for (int s = tid; s < SPG_HOT_SLOTS; s += 1024) hk[s] = EMPTY_KEY;
-    if (tid == 0) { fill = 0; nh = 0; }
+    if (tid == 0) { fill = 0; nh = 0; nwide = 0; }
     __syncthreads();
     const int64_t S = n_rows < SPG_HOT_SAMPLE ? n_rows : SPG_HOT_SAMPLE;
     const int64_t stride = S > 0 ? n_rows / S : 1;
@@ -1092,7 +1092,15 @@ __global__ void __launch_bounds__(1024, 1) spg_hot_sample_kernel(const long long
     for (int64_t i0 = tid; i0 < S; i0 += 1024 * ILP) {
         long long kv[ILP];
 #pragma unroll
-        for (int u = 0; u < ILP; u++) { const int64_t i = i0 + (int64_t)u * 1024; kv[u] = i < S ? keys[i * stride] : EMPTY_KEY; }
+        for (int u = 0; u < ILP; u++) {
+            const int64_t i = i0 + (int64_t)u * 1024;
+            kv[u] = i < S ? keys[i * stride] : EMPTY_KEY;
+            // SPG-N (spgn.cuh): does this sampled row fit an (int32, int32) bucket row?
+            if (i < S) {
+                const long long v = vals ? vals[i * stride] : 0;
+                if (kv[u] != (long long)(int)kv[u] || (int)kv[u] == (int)0x80000000 || v != (long long)(int)v) atomicAdd(&nwide, 1u);
+            }
+        }
 #pragma unroll
         for (int u = 0; u < ILP; u++) {
             const long long k = kv[u];
@@ -1128,7 +1136,7 @@ __global__ void __launch_bounds__(1024, 1) spg_hot_sample_kernel(const long long
         __syncthreads();
     }
     for (int s = tid; s < SPG_HOT_SLOTS; s += 1024) hot_tab[s] = hk[s];
-    if (tid == 0) *n_hot = (int)nh;
+    if (tid == 0) { n_hot[0] = (int)nh; n_hot[1] = (int)nwide; }
 }
 
 // K1 (plain-load fallback, used when the inputs are not 16-byte aligned or B200_SPG_TMA=0): partition rows into owner
@@ -1637,6 +1645,7 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spg_aggregate_kernel(const __g
     }
 }
 
+#include "spgn.cuh"  // SPG-N: narrow (int32 key, int32 value) bucket rows: 32 instead of 48 B/row of HBM traffic
 #include "spgg.cuh"  // SPG-G: the same two kernels for nullable / 4-byte / mean / min / max signatures
 #include "spf.cuh"  // SPF: the fused persistent variant of the SM-partitioned path (one kernel, bucket hand-off through L2)
 
@@ -2175,6 +2184,17 @@ class GroupbyState {
             }
         }
         { const char* e2 = getenv("B200_SPG_TMA"); spg_use_tma = !(e2 && e2[0] == '0'); }
+        {   // SPG-N (spgn.cuh): narrow bucket rows
+            spgn_ns = ((int)(((size_t)max_smem - 64) / 12) - SPG_STASH) & ~1;
+            spgn_smem = (size_t)(spgn_ns + SPG_STASH) * 12 + 16;
+            const void* nk1[3] = {(const void*)spgn_partition_kernel<true, true>, (const void*)spgn_partition_kernel<true, false>, (const void*)spgn_partition_kernel<false, true>};
+            const void* nk2[3] = {(const void*)spgn_aggregate_kernel<true, true>, (const void*)spgn_aggregate_kernel<true, false>, (const void*)spgn_aggregate_kernel<false, true>};
+            spgn_enabled = true;
+            for (auto f : nk1) if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spgn_part_smem()) != cudaSuccess) { cudaGetLastError(); spgn_enabled = false; }
+            for (auto f : nk2) if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spgn_smem) != cudaSuccess) { cudaGetLastError(); spgn_enabled = false; }
+            const char* e8 = getenv("B200_SPG_NARROW");
+            if (e8 && e8[0] == '0') spgn_enabled = false;
+        }
         {   // SPG-G (spgg.cuh): generic signatures
             spgg_enabled = 2 * sms <= GEN_CLS;  // classes of K1g's counting sort: at least owners + owners
             const void* gp[6] = {(const void*)spgg_partition_kernel<8, 8>, (const void*)spgg_partition_kernel<8, 4>, (const void*)spgg_partition_kernel<8, 0>,
@@ -2210,6 +2230,14 @@ class GroupbyState {
     }
 
     bool spg_use_tma = true, lc_enabled = true, lowcard_small = false;
+    // SPG-N: narrow bucket rows (spgn.cuh)
+    int spgn_ns = 0;
+    size_t spgn_smem = 0;
+    bool spgn_enabled = false;
+    int spg_sample_wide = -1;  // sampled rows of the first launch that do NOT fit (int32 key, int32 value); -1 = not sampled
+    int64_t spgn_launches = 0;
+    static size_t spgn_part_smem() { return (size_t)SPGN_TILE * (16 + 8 + 1) + SPG_MAX_OWNERS * 16 + 16 + (2 * SPG_MAX_OWNERS + 4) * 4 + 256; }
+    int64_t spgn_group_capacity() const { return (int64_t)spg_owners * (spgn_ns * 7 / 10); }
     int spgg_ns[4] = {0, 0, 0, 0};  // K2g table slots, by slot layout v = (min/max fields) + 2 * (NA-value counter)
     size_t spgg_smem[4] = {0, 0, 0, 0};
     bool spgg_enabled = true;      // B200_SPG_GEN=0 disables the generic SM-partitioned path
@@ -2242,10 +2270,12 @@ class GroupbyState {
     long long* h_spg = nullptr;  // pinned: [slot][8] counter snapshots
     cudaEvent_t spg_ev[2] = {nullptr, nullptr};
 
+    int64_t spgn_wide_rows = 0;  // rows that did not fit the narrow format so far (device counter 5)
     void spg_finish(int slot, int sum_j, int cnt_j) {
         B200_CUDA(cudaEventSynchronize(spg_ev[slot]));
         const long long* hc = h_spg + slot * 8;
         n_groups = hc[0];
+        spgn_wide_rows = hc[5];
         int64_t nr = hc[1 + 5 * slot];  // retry rows of that launch: counters[1] (slot 0) / counters[6] (slot 1)
         while (nr > 0) {
             // rows / partials that found the global table full: grow, then merge them like received partial rows
@@ -2352,19 +2382,35 @@ class GroupbyState {
                 int g1 = (int)std::min<int64_t>((int64_t)sms * SPG_PCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
                 const bool tma = spg_use_tma && (((uintptr_t)a.keys & 15) == 0) && (a.vals == nullptr || ((uintptr_t)a.vals & 15) == 0);
                 int g2 = (int)std::min<int64_t>((int64_t)sms * SPG_TCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
-                if (tma && spg_hot_enabled && !spg_hot_sampled) {
-                    // once per state: count a strided sample of this launch's keys, read back how many heavy hitters it found
+                if (tma && !spg_hot_sampled) {
+                    // once per state: count a strided sample of this launch's keys (heavy hitters) and test the sampled rows against
+                    // the narrow-row format; the host reads back both verdicts
                     int* d_nhot = (int*)(d_hot.as<long long>() + SPG_HOT_SLOTS);
-                    spg_hot_sample_kernel<<<1, 1024, SPG_HOT_SAMPLE_SMEM, stream>>>(a.keys, rows, d_hot.as<long long>(), d_nhot);
-                    B200_CUDA(cudaMemcpyAsync(h_spg + 16, d_nhot, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    spg_hot_sample_kernel<<<1, 1024, SPG_HOT_SAMPLE_SMEM, stream>>>(a.keys, a.vals, rows, d_hot.as<long long>(), d_nhot);
+                    B200_CUDA(cudaMemcpyAsync(h_spg + 16, d_nhot, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
                     B200_CUDA(cudaStreamSynchronize(stream));
-                    spg_n_hot = *(int*)(h_spg + 16);
+                    spg_n_hot = spg_hot_enabled ? ((int*)(h_spg + 16))[0] : 0;
+                    spg_sample_wide = ((int*)(h_spg + 16))[1];
                     spg_hot_sampled = true;
                     launches++;
                 }
                 const bool hot = tma && spg_hot_enabled && spg_n_hot > 0;
                 if (hot) { a.hot_tab = d_hot.as<long long>(); a.n_hot = (const int*)(d_hot.as<long long>() + SPG_HOT_SLOTS); }
                 const size_t tsm = spg_tma_smem(hot);
+                // SPG-N: the sample found only rows that fit (int32 key, int32 value), and the rows that did not so far are rare
+                const bool narrow = spgn_enabled && tma && !hot && !use_static && spg_sample_wide == 0 && spgn_wide_rows * 64 <= rows_consumed;
+                if (narrow) {
+                    a.ns = spgn_ns;
+                    const int64_t est_n = std::max<int64_t>(est_groups, 1);
+                    a.n_pass = (int)std::min<int64_t>(SPG_MAX_PASSES, std::max<int64_t>(1, (est_n + spgn_group_capacity() - 1) / spgn_group_capacity()));
+                    a.bucket_cap = bucket_cap & ~1ll;
+                    const size_t nsm = spgn_part_smem();
+                    const int g2 = (int)std::min<int64_t>((int64_t)sms * SPGN_CTAS, (rows + SPGN_TILE - 1) / SPGN_TILE);
+                    if (sum_j >= 0 && cnt_j >= 0) { spgn_partition_kernel<true, true><<<g2, SPG_TTHREADS, nsm, stream>>>(a); spgn_aggregate_kernel<true, true><<<spg_owners, SPG_THREADS, spgn_smem, stream>>>(a); }
+                    else if (sum_j >= 0) { spgn_partition_kernel<true, false><<<g2, SPG_TTHREADS, nsm, stream>>>(a); spgn_aggregate_kernel<true, false><<<spg_owners, SPG_THREADS, spgn_smem, stream>>>(a); }
+                    else { spgn_partition_kernel<false, true><<<g2, SPG_TTHREADS, nsm, stream>>>(a); spgn_aggregate_kernel<false, true><<<spg_owners, SPG_THREADS, spgn_smem, stream>>>(a); }
+                    spgn_launches++;
+                } else
                 if (use_static) {
                     a.sub_cnt = d_sub_cnt.as<unsigned int>(); a.n_cta = g2; a.ns = spg_ns - SPG_STATIC_CNT_SLOTS;
                     const size_t ssm = spg_tma_smem(true);
@@ -3217,6 +3263,7 @@ int64_t b200_groupby_get_metric(void* state, int32_t which) {
         case 10: return s->lc_launches;
         case 11: return s->co_batches;
         case 12: return s->spgg_launches;
+        case 14: return s->spgn_launches;
         case 13: { cudaSetDevice(s->device); s->read_counters(); return s->n_groups + s->untracked_groups; }  // exact (synchronises the stream)
         case 100: s->profiling = true; return 0;
         default: return -1;

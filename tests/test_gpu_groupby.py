@@ -516,3 +516,35 @@ def test_nunique_vs_pandas(gpu_lib, to_device, dropna):
     exp["o3"] = g.size()["size"].values
     exp["o4"] = exp["o0"]
     assert_frames_equal(positional(got), positional(exp))
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("funcs", [("sum", "count"), ("sum",), ("size",)])
+def test_narrow_row_sm_partitioned_path_exact_with_wide_stragglers(gpu_lib, oracle, funcs):
+    """SPG-N (spgn.cuh): when the sampled rows all fit (int32 key, int32 value) the owner buckets carry 8-byte rows (metric 14).
+    Rows that do not fit — here a few thousand the sample cannot see: keys beyond 2^40, the key INT32_MIN, values beyond 2^35,
+    negative everything — take the direct path inside K1n; the result is bit-exact either way (int64 sums wrap mod 2^64)."""
+    from bodo_b200.streaming.groupby import (delete_groupby_state, get_metric, groupby_build_consume_batch,
+                                             groupby_produce_output_batch, init_groupby_state)
+    from tests.helpers import table_to_device
+    rng = np.random.default_rng(8)
+    n, ng = 32768 * 80, 200_000   # the sampler looks at rows 0, 80, 160, ...
+    k = rng.integers(-ng // 2, ng // 2, n).astype(np.int64)
+    v = rng.integers(-(1 << 31), (1 << 31) - 1, n).astype(np.int64)
+    idx = np.arange(n)
+    w = (idx % 80 == 3) & (idx < 400_000)          # 5000 rows outside the narrow format, none of them sampled
+    k[w & (idx % 3 == 0)] += 1 << 41
+    k[w & (idx % 3 == 1)] = np.iinfo(np.int32).min
+    v[w & (idx % 3 == 2)] = (1 << 36) + idx[w & (idx % 3 == 2)]
+    v[w & (idx % 7 == 0)] = -(1 << 62)             # sums wrap
+    t = Table.from_pandas(pd.DataFrame({"k": k, "v": v}))
+    nf = len(funcs)
+    st = init_groupby_state(-1, (0,), funcs, tuple(range(nf + 1)) if "size" not in funcs else (0, 0), (1,) * (0 if funcs == ("size",) else nf),
+                            expected_groups=ng, output_batch_size=1 << 30)
+    groupby_build_consume_batch(st, table_to_device(t), True, True)
+    used = get_metric(st, 14)
+    out, _ = groupby_produce_output_batch(st, True)
+    got = out.to_pandas()
+    delete_groupby_state(st)
+    assert used >= 1, "the narrow-row kernels were expected to run for this shape"
+    assert_frames_equal(positional(got), oracle_groupby_frame(oracle, t, 0, list(funcs), [None if f == "size" else 1 for f in funcs]))
