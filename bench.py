@@ -37,7 +37,9 @@ BYTES_PER_ROW = 16  # algorithmic bytes of the hash-aggregate scan (SURVEY.md §
 # direct: profiles/r01_direct_ncu_summary.txt (2^27-row launch, bucketized variant): 10.99 + 0.18 GB.
 # Both are DRAM bytes per ROW of a launch (measured bytes / rows of the captured launch); one launch of the timed run
 # moves that figure x its own row count (launches are 2^27 rows now, the captures above were taken on 2^26 / 2^27).
-TRAFFIC_PER_ROW = {"spg": 3.220e9 / (1 << 26), "direct": 11.17e9 / (1 << 27)}
+# spgn (narrow bucket rows, the path the default workload takes since round 2): profiles/r02_spgn_ncu_launches.txt, 2^27-row launch
+# pair: K1n 2.149 + 1.045 GB, K2n 1.124 + 0.003 GB = 4.32 GB = 32.2 B/row (16 read + 8 bucket write + 8 bucket read by design).
+TRAFFIC_PER_ROW = {"spg": 3.220e9 / (1 << 26), "spgn": 4.321e9 / (1 << 27), "direct": 11.17e9 / (1 << 27)}
 
 
 def parse_args():
@@ -282,6 +284,7 @@ def main():
                 stats["consume_us"] = G.get_metric(st, 6)
                 stats["consume_launches"] = G.get_metric(st, 7)
                 stats["spg_launches"] = G.get_metric(st, 8)
+                stats["spgn_launches"] = G.get_metric(st, 14)
         G.delete_groupby_state(st)
         return res
 
@@ -378,8 +381,11 @@ def main():
     n_launch = max(stats.get("consume_launches", 1), 1)
     achieved = (BYTES_PER_ROW * n_local / 1e9) / (kern_us * 1e-6) if kern_us else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": TRAFFIC_PER_ROW["spg" if stats.get("spg_launches") else "direct"] * n_local / n_launch, "peak_kind": peak_kind,
-                "kernel": ("spg_partition_tma_kernel<true,true> + spg_aggregate_kernel<true,true> (one launch = the pair)"
+                "traffic": TRAFFIC_PER_ROW["spgn" if stats.get("spgn_launches") else "spg" if stats.get("spg_launches") else "direct"] * n_local / n_launch,
+                "peak_kind": peak_kind,
+                "kernel": ("spgn_partition_kernel<true,true> + spgn_aggregate_kernel<true,true> (narrow bucket rows; one launch = the pair)"
+                           if stats.get("spgn_launches") else
+                           "spg_partition_tma_kernel<true,true> + spg_aggregate_kernel<true,true> (one launch = the pair)"
                            if stats.get("spg_launches") else "groupby_consume_i64_sumcount_kernel<true,true>"),
                 "launches_per_step": n_launch, "avg_launch_ms": kern_us / 1e3 / n_launch,
                 "algorithmic_bytes_per_launch": BYTES_PER_ROW * n_local / n_launch}

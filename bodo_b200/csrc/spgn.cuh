@@ -209,10 +209,9 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spgn_aggregate_kernel(const __
     const int2* src = reinterpret_cast<const int2*>(a.bucket) + (size_t)me * a.bucket_cap;  // bucket_cap is even: 16-byte aligned
     constexpr int U = 4;  // rows per thread per iteration, as two 16-byte loads of two adjacent rows
     // unit = two adjacent rows; units of this thread: first + j * SPG_THREADS, j = 0 .. U/2 - 1
-    auto process = [&](unsigned long long first, unsigned int pass, auto full_tag) {
+    // rows of one iteration: U/2 units of two adjacent rows, unit index first + j * SPG_THREADS
+    auto load_rows = [&](unsigned long long first, int2 (&row)[U], auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
-        int2 row[U];
-        int sl[U];
 #pragma unroll
         for (int j = 0; j < U / 2; j++) {
             const unsigned long long r = 2 * (first + (unsigned long long)j * SPG_THREADS);
@@ -222,6 +221,10 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spgn_aggregate_kernel(const __
                 row[2 * j] = make_int2(q.x, q.y); row[2 * j + 1] = make_int2(q.z, q.w);
             } else if (r < n_in) row[2 * j] = __ldcs(src + r);
         }
+    };
+    auto process = [&](const int2 (&row)[U], unsigned int pass, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        int sl[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint64_t h = spg_hash((long long)row[u].x);
@@ -251,8 +254,23 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spgn_aggregate_kernel(const __
     for (unsigned int pass = 0; pass < NP; pass++) {
         for (int s = tid; s < NT; s += SPG_THREADS) { skeys[s] = SPGN_EMPTY; slo[s] = 0x80000000u; scnt[s] = 0; }
         __syncthreads();
-        for (unsigned long long ub = 0; ub < full_units; ub += ustep) process(ub + tid, pass, std::true_type{});
-        for (unsigned long long ub = full_units; 2 * ub < n_in; ub += ustep) process(ub + tid, pass, std::false_type{});
+        // software pipeline: the next iteration's bucket rows are in flight while the current ones are aggregated (the wait for these
+        // loads was the largest single stall of the unpipelined loop, 20 % of the samples)
+        if (full_units > 0) {
+            int2 cur[U], nxt[U];
+            load_rows(tid, cur, std::true_type{});
+            for (unsigned long long ub = 0; ub < full_units; ub += ustep) {
+                if (ub + ustep < full_units) load_rows(ub + ustep + tid, nxt, std::true_type{});
+                process(cur, pass, std::true_type{});
+#pragma unroll
+                for (int u = 0; u < U; u++) cur[u] = nxt[u];
+            }
+        }
+        for (unsigned long long ub = full_units; 2 * ub < n_in; ub += ustep) {
+            int2 tail[U];
+            load_rows(ub + tid, tail, std::false_type{});
+            process(tail, pass, std::false_type{});
+        }
         __syncthreads();
         for (int s = tid; s < NT; s += SPG_THREADS) {
             const int key = skeys[s];
