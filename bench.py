@@ -37,9 +37,10 @@ BYTES_PER_ROW = 16  # algorithmic bytes of the hash-aggregate scan (SURVEY.md §
 # direct: profiles/r01_direct_ncu_summary.txt (2^27-row launch, bucketized variant): 10.99 + 0.18 GB.
 # Both are DRAM bytes per ROW of a launch (measured bytes / rows of the captured launch); one launch of the timed run
 # moves that figure x its own row count (launches are 2^27 rows now, the captures above were taken on 2^26 / 2^27).
-# spgn (narrow bucket rows, the path the default workload takes since round 2): profiles/r02_spgn_ncu_launches.txt, 2^27-row launch
-# pair: K1n 2.149 + 1.045 GB, K2n 1.124 + 0.003 GB = 4.32 GB = 32.2 B/row (16 read + 8 bucket write + 8 bucket read by design).
-TRAFFIC_PER_ROW = {"spg": 3.220e9 / (1 << 26), "spgn": 4.321e9 / (1 << 27), "direct": 11.17e9 / (1 << 27)}
+# spgn (narrow bucket rows, the path the default workload takes since round 2): profiles/r02_launches.txt (105 launches of the
+# shipping 2^27-row kernels): K1n 2.133 + 1.029 GB, K2n 1.116 + 0.000 GB = 4.279 GB = 31.9 B/row (16 read + 8 bucket write +
+# 8 bucket read by design).
+TRAFFIC_PER_ROW = {"spg": 3.220e9 / (1 << 26), "spgn": 4.279e9 / (1 << 27), "direct": 11.17e9 / (1 << 27)}
 
 
 def parse_args():
