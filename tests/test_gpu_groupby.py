@@ -528,11 +528,11 @@ def test_narrow_row_sm_partitioned_path_exact_with_wide_stragglers(gpu_lib, orac
                                              groupby_produce_output_batch, init_groupby_state)
     from tests.helpers import table_to_device
     rng = np.random.default_rng(8)
-    n, ng = 32768 * 80, 200_000   # the sampler looks at rows 0, 80, 160, ...
+    n, ng = 32768 * 80, 200_000   # the sampler looks at 32 blocks of 1024 rows: [b * n / 32, b * n / 32 + 1024)
     k = rng.integers(-ng // 2, ng // 2, n).astype(np.int64)
     v = rng.integers(-(1 << 31), (1 << 31) - 1, n).astype(np.int64)
     idx = np.arange(n)
-    w = (idx % 80 == 3) & (idx < 400_000)          # 5000 rows outside the narrow format, none of them sampled
+    w = (idx % 80 == 3) & (idx < 400_000) & (idx % (n // 32) >= 1024)  # ~5000 rows outside the narrow format, none of them sampled
     k[w & (idx % 3 == 0)] += 1 << 41
     k[w & (idx % 3 == 1)] = np.iinfo(np.int32).min
     v[w & (idx % 3 == 2)] = (1 << 36) + idx[w & (idx % 3 == 2)]
