@@ -20,13 +20,15 @@
 #include <memory>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace b200 {
 
 constexpr long long EMPTY_KEY = (long long)0x8000000000000000ULL;  // INT64_MIN marks a free slot
 constexpr int MAX_OPS = 16;
-constexpr int64_t CHUNK_ROWS = 1ll << 27;  // rows per kernel launch (bounds the fail list at 512 MiB)
+constexpr int64_t CHUNK_ROWS = 1ll << 28;  // rows per consume chunk (bounds the fail list of the direct path at 1 GiB)
 
 enum OpKind : int { K_SUM_I64 = 0, K_SUM_F64, K_COUNT, K_SIZE, K_MEAN, K_MIN_I64, K_MAX_I64, K_MIN_F64, K_MAX_F64,
                     K_SUMSQ_F64, K_SUMCUBE_F64,  // hidden accumulators: sum of squares / cubes (as double) of the non-NA values
@@ -75,9 +77,14 @@ __device__ __forceinline__ uint64_t find_or_insert(long long* __restrict__ tkeys
         long long k = __ldcg(tkeys + s);
         if (k == key) return s;
         if (k == EMPTY_KEY) {
-            // take a ticket first so the table can never exceed group_limit (probing always terminates)
+            // take a ticket first so the table can never exceed group_limit (probing always terminates).  The lanes of the warp
+            // that stand here together take their tickets with ONE atomic (coalesced group): a flush of 10^6 new groups is 10^6
+            // tickets on a single address otherwise (measured 0.17 ms per operator state)
             if (group_limit >= 0) {
-                long long t = atomicAdd((unsigned long long*)&counters[0], 1ull);
+                const cooperative_groups::coalesced_group cgp = cooperative_groups::coalesced_threads();
+                long long t = 0;
+                if (cgp.thread_rank() == 0) t = (long long)atomicAdd((unsigned long long*)&counters[0], (unsigned long long)cgp.size());
+                t = cgp.shfl(t, 0) + (long long)cgp.thread_rank();
                 if (t >= group_limit) {
                     atomicAdd((unsigned long long*)&counters[0], (unsigned long long)-1ll);
                     return ~0ull;
@@ -1032,6 +1039,7 @@ struct SpgArgs {
     // inside the owner's bucket, so K1 needs no global run-reservation atomics; sub_cnt[owner * n_cta + cta] = rows written
     unsigned int* sub_cnt;
     int n_cta;
+    int reserve_tickets;  // K2n flush: the global table is empty — a CTA reserves the group tickets of all its slots with one atomic
 };
 
 // cheap in-kernel hash for owner / shared-table slot (placement inside one GPU is free to choose; the rank
@@ -2188,7 +2196,7 @@ class GroupbyState {
         }
         { const char* e2 = getenv("B200_SPG_TMA"); spg_use_tma = !(e2 && e2[0] == '0'); }
         {   // SPG-N (spgn.cuh): narrow bucket rows
-            spgn_ns = ((int)(((size_t)max_smem - 64) / 12) - SPG_STASH) & ~1;
+            spgn_ns = ((int)(((size_t)max_smem - 256) / 12) - SPG_STASH) & ~1;  // (K2n also has a few static shared words)
             spgn_smem = (size_t)(spgn_ns + SPG_STASH) * 12 + 16;
             const void* nk1[3] = {(const void*)spgn_partition_kernel<true, true>, (const void*)spgn_partition_kernel<true, false>, (const void*)spgn_partition_kernel<false, true>};
             const void* nk2[3] = {(const void*)spgn_aggregate_kernel<true, true>, (const void*)spgn_aggregate_kernel<true, false>, (const void*)spgn_aggregate_kernel<false, true>};
@@ -2325,10 +2333,26 @@ class GroupbyState {
         struct Acc2 { double& t; double t0; ~Acc2() { t += now() - t0; } } acc2{t_spg, tspg0};
         read_counters();  // exact group count before the first launch
         n_groups_bound = n_groups;
+        const bool tma_all = spg_use_tma && (((uintptr_t)keys & 15) == 0) && (vals == nullptr || ((uintptr_t)vals & 15) == 0);
+        if (!lowcard && tma_all && !spg_hot_sampled) {
+            // once per state: count a sample of this call's keys (heavy hitters) and test the sampled rows against the narrow-row
+            // format; the host reads back both verdicts
+            int* d_nhot = (int*)(d_hot.as<long long>() + SPG_HOT_SLOTS);
+            spg_hot_sample_kernel<<<1, 1024, SPG_HOT_SAMPLE_SMEM, stream>>>(keys, vals, n, d_hot.as<long long>(), d_nhot);
+            B200_CUDA(cudaMemcpyAsync(h_spg + 16, d_nhot, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            B200_CUDA(cudaStreamSynchronize(stream));
+            spg_n_hot = spg_hot_enabled ? ((int*)(h_spg + 16))[0] : 0;
+            spg_sample_wide = ((int*)(h_spg + 16))[1];
+            spg_hot_sampled = true;
+            launches++;
+        }
+        // narrow bucket rows are half the bytes: twice the rows per launch for the same scratch, half the per-launch flushes
+        const bool narrow_call = spgn_enabled && !lowcard && tma_all && !spg_static && spg_n_hot == 0 && spg_sample_wide == 0;
+        const int64_t launch_rows = narrow_call ? 2 * SPG_LAUNCH_ROWS : SPG_LAUNCH_ROWS;
         int64_t li = 0;
-        for (int64_t r0 = 0; r0 < n; r0 += SPG_LAUNCH_ROWS, li++) {
+        for (int64_t r0 = 0; r0 < n; r0 += launch_rows, li++) {
             int slot = (int)(li & 1);
-            int64_t rows = std::min(SPG_LAUNCH_ROWS, n - r0);
+            int64_t rows = std::min(launch_rows, n - r0);
             // no pre-growing: a flush that finds the global table at its limit lands in the retry list and is merged
             // after the table grew (spg_finish), exactly like rows of the direct path
             // uniform keys put rows / owners rows in every bucket (sd = sqrt of that); 12.5 % + 4096 rows head room,
@@ -2385,18 +2409,6 @@ class GroupbyState {
                 int g1 = (int)std::min<int64_t>((int64_t)sms * SPG_PCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
                 const bool tma = spg_use_tma && (((uintptr_t)a.keys & 15) == 0) && (a.vals == nullptr || ((uintptr_t)a.vals & 15) == 0);
                 int g2 = (int)std::min<int64_t>((int64_t)sms * SPG_TCTAS, (rows + SPG_TILE - 1) / SPG_TILE);
-                if (tma && !spg_hot_sampled) {
-                    // once per state: count a strided sample of this launch's keys (heavy hitters) and test the sampled rows against
-                    // the narrow-row format; the host reads back both verdicts
-                    int* d_nhot = (int*)(d_hot.as<long long>() + SPG_HOT_SLOTS);
-                    spg_hot_sample_kernel<<<1, 1024, SPG_HOT_SAMPLE_SMEM, stream>>>(a.keys, a.vals, rows, d_hot.as<long long>(), d_nhot);
-                    B200_CUDA(cudaMemcpyAsync(h_spg + 16, d_nhot, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-                    B200_CUDA(cudaStreamSynchronize(stream));
-                    spg_n_hot = spg_hot_enabled ? ((int*)(h_spg + 16))[0] : 0;
-                    spg_sample_wide = ((int*)(h_spg + 16))[1];
-                    spg_hot_sampled = true;
-                    launches++;
-                }
                 const bool hot = tma && spg_hot_enabled && spg_n_hot > 0;
                 if (hot) { a.hot_tab = d_hot.as<long long>(); a.n_hot = (const int*)(d_hot.as<long long>() + SPG_HOT_SLOTS); }
                 const size_t tsm = spg_tma_smem(hot);
@@ -2404,6 +2416,7 @@ class GroupbyState {
                 const bool narrow = spgn_enabled && tma && !hot && !use_static && spg_sample_wide == 0 && spgn_wide_rows * 64 <= rows_consumed;
                 if (narrow) {
                     a.ns = spgn_ns;
+                    a.reserve_tickets = (n_groups_bound == 0 && li == 0) ? 1 : 0;  // first flush into an empty table
                     const int64_t est_n = std::max<int64_t>(est_groups, 1);
                     a.n_pass = (int)std::min<int64_t>(SPG_MAX_PASSES, std::max<int64_t>(1, (est_n + spgn_group_capacity() - 1) / spgn_group_capacity()));
                     a.bucket_cap = bucket_cap & ~1ll;

@@ -18,6 +18,23 @@ constexpr int SPGN_EMPTY = (int)0x80000000;
 constexpr int SPGN_TILE = SPGN_TILE_ROWS;            // rows per K1n tile (8-byte staged rows leave room for twice the 16-byte kernels' tile)
 constexpr int SPGN_CTAS = SPGN_TILE == 4096 ? 2 : 3;  // K1n CTAs per SM
 
+// find-or-insert for a caller that already holds a group ticket: `inserted` says whether THIS call created the group (else the
+// ticket goes back).  The table cannot be full: tickets bound the number of groups by cap / 2.
+__device__ __forceinline__ uint64_t spgn_insert_ticketed(long long* __restrict__ tkeys, uint64_t cap, long long key, bool& inserted) {
+    const uint64_t mask = cap - 1;
+    uint64_t s = (key_hash(key) >> 32) & mask;
+    inserted = false;
+    while (true) {
+        long long k = __ldcg(tkeys + s);
+        if (k == EMPTY_KEY) {
+            k = (long long)atomicCAS((unsigned long long*)(tkeys + s), (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+            if (k == EMPTY_KEY) { inserted = true; return s; }
+        }
+        if (k == key) return s;
+        s = (s + 1) & mask;
+    }
+}
+
 template <bool HAS_SUM, bool HAS_CNT>
 __global__ void __launch_bounds__(SPG_TTHREADS, SPGN_CTAS) spgn_partition_kernel(const __grid_constant__ SpgArgs a) {
     extern __shared__ __align__(128) unsigned char smem_n_raw[];
@@ -272,11 +289,45 @@ __global__ void __launch_bounds__(SPG_THREADS, 1) spgn_aggregate_kernel(const __
             process(tail, pass, std::false_type{});
         }
         __syncthreads();
+        // flush.  First flush of a state (empty global table, a.reserve_tickets): every occupied slot is a NEW group, and 10^6
+        // per-insert tickets on one counter cost ~0.2 ms — the CTA takes the tickets of all its slots with ONE atomic and returns
+        // the few it did not need (a key that sits in two slots, or that the direct path inserted meanwhile).
+        __shared__ unsigned int fl_occ, fl_dup;
+        __shared__ int fl_reserved;
+        if (tid == 0) { fl_occ = 0; fl_dup = 0; fl_reserved = 0; }
+        __syncthreads();
+        if (a.reserve_tickets && a.group_limit >= 0) {
+            unsigned int mine = 0;
+            for (int s = tid; s < NT; s += SPG_THREADS) mine += skeys[s] != SPGN_EMPTY;
+            for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+            if ((tid & 31) == 0 && mine) atomicAdd(&fl_occ, mine);
+            __syncthreads();
+            if (tid == 0 && fl_occ) {
+                const long long t = (long long)atomicAdd((unsigned long long*)&a.counters[0], (unsigned long long)fl_occ);
+                if (t + (long long)fl_occ <= a.group_limit) fl_reserved = 1;
+                else atomicAdd((unsigned long long*)&a.counters[0], (unsigned long long)(-(long long)fl_occ));  // no room: per-insert tickets
+            }
+            __syncthreads();
+        }
+        const bool reserved = fl_reserved != 0;
+        unsigned int dup = 0;
         for (int s = tid; s < NT; s += SPG_THREADS) {
             const int key = skeys[s];
             if (key == SPGN_EMPTY) continue;
             const unsigned long long sum = (unsigned long long)slo[s] - 0x80000000ull;  // remove the bias (wraps mod 2^64)
-            spg_direct_apply<HAS_SUM, HAS_CNT>(a, (long long)key, sum, (unsigned long long)scnt[s]);
+            if (!reserved) { spg_direct_apply<HAS_SUM, HAS_CNT>(a, (long long)key, sum, (unsigned long long)scnt[s]); continue; }
+            // ticket already held: insert without the limit; a key that was there already gives its ticket back
+            bool inserted;
+            const uint64_t sl = spgn_insert_ticketed(a.tkeys, a.cap, (long long)key, inserted);
+            if (!inserted) dup++;
+            if (HAS_SUM && sum) atomicAdd(a.acc_sum + sl, sum);
+            if (HAS_CNT && scnt[s]) atomicAdd(a.acc_cnt + sl, (unsigned long long)scnt[s]);
+        }
+        if (reserved) {
+            for (int d = 16; d; d >>= 1) dup += __shfl_xor_sync(0xffffffffu, dup, d);
+            if ((tid & 31) == 0 && dup) atomicAdd(&fl_dup, dup);
+            __syncthreads();
+            if (tid == 0 && fl_dup) atomicAdd((unsigned long long*)&a.counters[0], (unsigned long long)(-(long long)fl_dup));
         }
         __syncthreads();
     }
