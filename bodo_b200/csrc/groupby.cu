@@ -2416,7 +2416,11 @@ class GroupbyState {
                 const bool narrow = spgn_enabled && tma && !hot && !use_static && spg_sample_wide == 0 && spgn_wide_rows * 64 <= rows_consumed;
                 if (narrow) {
                     a.ns = spgn_ns;
-                    a.reserve_tickets = (n_groups_bound == 0 && li == 0) ? 1 : 0;  // first flush into an empty table
+                    // first flush into an empty table: per-CTA ticket reservation, but only with >= 25 % head room under the group
+                    // limit — a reservation transiently over-counts (slots that hold one key twice), and a CTA that then finds the
+                    // limit reached would send its groups to the retry list and make the host grow the table for nothing (seen on
+                    // 8 GPUs: 1 M groups against a limit of 2^20 cost 1.4 ms per state in some runs)
+                    a.reserve_tickets = (n_groups_bound == 0 && li == 0 && est_groups > 0 && est_groups + est_groups / 4 <= (int64_t)(cap / 2)) ? 1 : 0;
                     const int64_t est_n = std::max<int64_t>(est_groups, 1);
                     a.n_pass = (int)std::min<int64_t>(SPG_MAX_PASSES, std::max<int64_t>(1, (est_n + spgn_group_capacity() - 1) / spgn_group_capacity()));
                     a.bucket_cap = bucket_cap & ~1ll;
