@@ -98,6 +98,19 @@ class ClockSampler:
                                        "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        # wait for the first sample: nvidia-smi's start-up (NVML initialisation over all GPUs of the box, 0.2 - 1 s) takes driver
+        # locks that stall CUDA calls of the benchmark process; it has to be over before the timed region starts (an 8-GPU run
+        # whose 30 ms timed region overlapped it lost 1.4 ms per step)
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < 5.0:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    break
+            except OSError:
+                pass
+            if self.p.poll() is not None:
+                break
+            time.sleep(0.02)
 
     def stop(self):
         if self.p is None:
