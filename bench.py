@@ -344,6 +344,7 @@ def main():
     # the clock sampler starts before the warm-up (nvidia-smi needs ~0.2 s to deliver its first sample and a short timed region
     # would otherwise end before it): warm-up and timed steps are the same workload, every sample is taken under load
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()  # rank 0 may have waited for nvidia-smi: line the ranks up again before the first collective step
     for _ in range(max(args.warmup, 0)):
         one_step(table)
     barrier()
