@@ -13,6 +13,13 @@ the batch: init state -> consume all local rows -> (exchange) -> finalize -> pro
   cpu_baseline  the CPU oracle (reference algorithm shape, one rank per host thread) on a bounded sample
 
 `--impl reference` times only that CPU restatement (the reference runtime cannot be built here: no MPI).
+
+The line also carries `config.no_hint` (the same steps without the expected_groups hint, which the reference's API does not
+have; `--no-hint` makes that the headline run).  Other workloads, each printing the same kind of line:
+  --workload join                           BASELINE.json configs[2], benchmarks/join_bench.py
+  --workload shuffle                        raw-row variant of configs[3], benchmarks/shuffle_bench.py
+  --aggs F1,F2.. [--nullable] [--key-dtype int32] [--val-dtype int32]
+                                            other signatures of configs[1], benchmarks/groupby_variant_bench.py
 """
 
 from __future__ import annotations
