@@ -24,6 +24,10 @@ FT = {"sum", "count", "size", "mean", "min", "max"}
 
 
 def run(args, ClockSampler, peaks):
+    if args.impl == "reference":  # the CPU arm exists for the headline workload (bench.py) and the join only
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "no CPU arm for the groupby variant workload; see bench.py --impl reference"}), flush=True)
+        return
     import torch
 
     from bodo_b200 import _lib, synth

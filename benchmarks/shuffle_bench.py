@@ -25,6 +25,10 @@ UNIT = "rows/s"
 
 
 def run(args, ClockSampler, peaks):
+    if args.impl == "reference":  # the CPU arm exists for the headline workload (bench.py) and the join only
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "no CPU arm for the shuffle workload; see bench.py --impl reference"}), flush=True)
+        return
     import torch
     import torch.distributed as dist
 
